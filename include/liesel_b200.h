@@ -1,0 +1,200 @@
+/*
+ * liesel_b200.h — C ABI of the B200-native hot path behind Liesel's model interface.
+ *
+ * What this boundary replaces in the reference (liesel 0.5.1, paths relative to the
+ * reference checkout):
+ *
+ *   - the value the kernels read through `ModelInterface.log_prob`
+ *     (src/liesel/goose/types.py:72-102) after `update_state`, i.e. what
+ *     `LieselInterface.update_state/log_prob` (src/liesel/goose/interface.py:284-313)
+ *     obtain from `Model.update_state` (src/liesel/model/model.py:2786-2865), and its
+ *     gradient as taken by `jax.value_and_grad` inside NUTS/HMC
+ *     (src/liesel/goose/nuts.py:193-194,254-260; src/liesel/goose/hmc.py:168-169,231-238);
+ *   - the IWLS score / information / Cholesky of `IWLSKernel._score/_chol_info`
+ *     (src/liesel/goose/iwls.py:206-243), for which the reference offers the
+ *     `chol_info_fn` hook (src/liesel/goose/iwls.py:130-145);
+ *   - the quadratic form of `tau2_gibbs_kernel` (src/liesel/model/distreg.py:277-297);
+ *   - the B-spline basis of `basis_matrix` (src/liesel/contrib/splines.py:109-198).
+ *
+ * Conventions. Every pointer named in a *_desc struct or passed to a compute call is a
+ * DEVICE pointer unless stated otherwise. Compute calls are asynchronous on `stream`,
+ * allocate nothing, never synchronise and never abort: they return a status code
+ * (0 = LSLB_OK). A plan is immutable after creation and may be used from several host
+ * threads at once, each with its own workspace. Data pointers in the model description
+ * are BORROWED: the caller owns them and must keep them alive while the plan is in use.
+ *
+ * Chains are batched: `C` chains are evaluated per call against one copy of the data.
+ * `params` is [C x P] row-major (one flat position per chain, coefficient blocks in the
+ * order of `lslb_model_desc.blocks`), `aux` is [C x A] row-major (one tau2 per penalised
+ * block that has `tau2_slot >= 0`).
+ */
+#ifndef LIESEL_B200_H
+#define LIESEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSLB_VERSION 100
+#define LSLB_MAX_BLOCKS 16
+#define LSLB_MAX_IWLS_P 64
+
+typedef struct CUstream_st* lslb_stream_t; /* == cudaStream_t */
+typedef struct lslb_plan lslb_plan;
+
+enum lslb_status {
+  LSLB_OK = 0,
+  LSLB_ERR_INVALID = 1,     /* bad argument / unsupported model structure */
+  LSLB_ERR_WORKSPACE = 2,   /* workspace too small */
+  LSLB_ERR_CUDA = 3,        /* a CUDA runtime call failed (see lslb_last_cuda_error) */
+  LSLB_ERR_UNSUPPORTED = 4  /* valid request this build does not implement */
+};
+
+enum lslb_dtype { LSLB_F32 = 0, LSLB_F64 = 1 };
+
+/* Response families (reference: tfd.<Dist>(...).log_prob(y) in Dist.update,
+ * src/liesel/model/nodes.py:1139-1152). */
+enum lslb_family {
+  LSLB_NORMAL = 0,    /* predictor 0 = loc (identity link), predictor 1 = log(scale) */
+  LSLB_BERNOULLI = 1, /* predictor 0 = logits */
+  LSLB_POISSON = 2    /* predictor 0 = log_rate */
+};
+
+/* Additive terms of a predictor (reference: smooth Calc `jnp.dot(X, beta)`,
+ * src/liesel/model/distreg.py:105,175, summed at :238-240). */
+enum lslb_kind {
+  LSLB_DENSE = 0,    /* X [n x ld] row-major, ncoef columns used */
+  LSLB_SPLINE = 1,   /* cubic B-spline in banded form: start[n], weights[n x 4] */
+  LSLB_GROUP = 2,    /* random intercept b[index[i]]; rows sorted by index */
+  LSLB_INTERCEPT = 3 /* all-ones column; nothing is read */
+};
+
+enum lslb_prior {
+  LSLB_PRIOR_NONE = 0,
+  LSLB_PRIOR_NORMAL = 1, /* elementwise Normal(m, s): distreg.py:102 */
+  LSLB_PRIOR_MVND = 2    /* MultivariateNormalDegenerate.from_penalty(0, tau2, K, rank):
+                            distreg.py:166-172, distributions/mvn_degen.py:209-287,436-444 */
+};
+
+typedef struct lslb_block_desc {
+  int32_t kind;       /* enum lslb_kind */
+  int32_t predictor;  /* 0 or 1 */
+  int32_t ncoef;      /* p (dense), k (spline), G (group), 1 (intercept) */
+  int32_t prior;      /* enum lslb_prior */
+  const void* data;   /* dense: X; spline: weights [n x 4]; else NULL */
+  const int32_t* index; /* spline: start [n]; group: idx [n] (ascending); else NULL */
+  int64_t ld;         /* dense: row stride of X in elements */
+  double prior_m;     /* Normal prior mean */
+  double prior_s;     /* Normal prior standard deviation */
+  const void* K;      /* MVND: penalty matrix [ncoef x ncoef] row-major, model dtype */
+  double rank;        /* MVND: rank of K (distreg.py:161) */
+  double log_pdet;    /* MVND: log pseudo-determinant of K (mvn_degen.py:32-56) */
+  int32_t tau2_slot;  /* MVND: column of `aux` holding tau2, or -1 for tau2_fixed */
+  int32_t has_ig;     /* MVND: add InverseGamma(ig_a, ig_b).log_prob(tau2) (distreg.py:162) */
+  double tau2_fixed;
+  double ig_a;
+  double ig_b;
+} lslb_block_desc;
+
+typedef struct lslb_model_desc {
+  int32_t dtype;        /* enum lslb_dtype: type of y, data, K, params, aux and outputs */
+  int32_t family;       /* enum lslb_family */
+  int64_t n;            /* rows */
+  const void* y;        /* response [n] */
+  double fixed_scale;   /* Normal without a predictor-1 block: constant scale */
+  double const_term;    /* cached log-probs of Dist nodes that never change */
+  int32_t nblocks;
+  int32_t reserved;
+  const lslb_block_desc* blocks; /* HOST array of nblocks entries */
+} lslb_model_desc;
+
+/* flags for compute calls */
+#define LSLB_SKIP_PRIOR 1u /* likelihood part only: for ranks > 0 under row sharding, where
+                              partial results are summed across ranks afterwards */
+
+int lslb_version(void);
+const char* lslb_status_string(int status);
+const char* lslb_last_cuda_error(void);
+
+/* Builds the immutable evaluation plan. Synchronous (setup time). */
+int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out);
+void lslb_plan_destroy(lslb_plan* plan);
+int lslb_plan_num_params(const lslb_plan* plan);
+int lslb_plan_num_aux(const lslb_plan* plan);
+/* Name of the kernel variant the plan dispatches to (static string). */
+const char* lslb_plan_variant(const lslb_plan* plan);
+
+/* Bytes of device scratch a compute call on C chains needs (max over all entry points). */
+size_t lslb_workspace_bytes(const lslb_plan* plan, int C);
+
+/*
+ * Log-posterior and gradient for C chains. Replaces one `update_state` + `log_prob`
+ * (+ reverse-mode gradient) of the reference per chain.
+ *   logp [C]; grad [C x P] or NULL for value only (mh_step, src/liesel/goose/mh.py:48-50).
+ */
+int lslb_logp_grad_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
+                       float* logp, float* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                       lslb_stream_t stream);
+int lslb_logp_grad_f64(const lslb_plan* plan, int C, const double* params, const double* aux,
+                       double* logp, double* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                       lslb_stream_t stream);
+
+/*
+ * IWLS quantities of ONE coefficient block (p = ncoef <= LSLB_MAX_IWLS_P) for C chains, in
+ * one pass over the rows:
+ *   score [C x p]     = d logp / d beta_block              (iwls.py:206-216,315)
+ *   info  [C x p x p] = -d2 logp / d beta_block^2, full symmetric, WITHOUT the ridge
+ *                       (iwls.py:232; observed information)
+ *   chol  [C x p x p] or NULL = lower Cholesky factor of info + 1e-6*mean(diag(info))*I
+ *                       (iwls.py:233-238); every entry NaN when not positive definite,
+ *                       like jnp.linalg.cholesky, so IWLSKernel._safe_chol still fires.
+ */
+int lslb_iwls_f32(const lslb_plan* plan, int C, int block, const float* params,
+                  const float* aux, float* score, float* info, float* chol, uint32_t flags,
+                  void* ws, size_t ws_bytes, lslb_stream_t stream);
+int lslb_iwls_f64(const lslb_plan* plan, int C, int block, const double* params,
+                  const double* aux, double* score, double* info, double* chol,
+                  uint32_t flags, void* ws, size_t ws_bytes, lslb_stream_t stream);
+
+/* Ridge + batched Cholesky alone (for info summed across ranks): chol may alias info. */
+int lslb_chol_f32(int C, int p, const float* info, float* chol, lslb_stream_t stream);
+int lslb_chol_f64(int C, int p, const double* info, double* chol, lslb_stream_t stream);
+
+/* beta_block^T K beta_block per chain, out [C] (tau2_gibbs_kernel, distreg.py:291). */
+int lslb_quadform_f32(const lslb_plan* plan, int C, int block, const float* params,
+                      float* out, lslb_stream_t stream);
+int lslb_quadform_f64(const lslb_plan* plan, int C, int block, const double* params,
+                      double* out, lslb_stream_t stream);
+
+/*
+ * IWLS proposal tail per chain (iwls.py:323-327 and :335-336; iwls_utils.py:14-70):
+ *   mu   = beta + (step^2 / 2) * solve(chol, score)
+ *   prop = mu + (chol/step)^{-T} z              (only when z != NULL)
+ *   logq = mvn_log_prob(x, mu, chol/step)       with x = prop (z != NULL) or x_eval
+ * beta, score, z, x_eval, prop are [C x p]; chol [C x p x p]; step, logq [C].
+ */
+int lslb_iwls_propose_f32(int C, int p, const float* beta, const float* score,
+                          const float* chol, const float* step, const float* z,
+                          const float* x_eval, float* prop, float* logq, lslb_stream_t stream);
+int lslb_iwls_propose_f64(int C, int p, const double* beta, const double* score,
+                          const double* chol, const double* step, const double* z,
+                          const double* x_eval, double* prop, double* logq,
+                          lslb_stream_t stream);
+
+/*
+ * Banded cubic B-spline basis (splines.py:73-106 recursion, half-open base case):
+ * start [n] = first column of the 4-wide window, weights [n x 4].
+ * The span is decided by comparing x against the stored knot array.
+ */
+int lslb_spline_basis_f32(const float* x, int64_t n, const float* knots, int nknots,
+                          int32_t* start, float* weights, lslb_stream_t stream);
+int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int nknots,
+                          int32_t* start, double* weights, lslb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIESEL_B200_H */

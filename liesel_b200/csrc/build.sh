@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libliesel_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+       -I ../../include -Xptxas -v --expt-relaxed-constexpr)
+SRCS=(plan.cu logp_grad.cu iwls.cu spline_basis.cu)
+mkdir -p build
+pids=()
+for s in "${SRCS[@]}"; do
+  o=build/${s%.cu}.o
+  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || prologue.cuh -nt $o || ../../include/liesel_b200.h -nt $o ]]; then
+    ( $NVCC "${FLAGS[@]}" -c "$s" -o "$o" > "build/${s%.cu}.log" 2>&1 || { cat "build/${s%.cu}.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libliesel_b200.so build/*.o -lcudart
+echo "built $(pwd)/libliesel_b200.so"

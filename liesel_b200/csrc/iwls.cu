@@ -1,0 +1,617 @@
+// IWLS score + observed information of ONE coefficient block for C chains in a single pass
+// over the rows, ridge + batched small Cholesky, the proposal tail and the Gibbs quadratic form.
+//
+// Replaces `grad(flat_log_prob_fn)` and `-jacfwd(grad(...))` of the reference
+// (src/liesel/goose/iwls.py:315-321), `_chol_info` (:218-243), `solve`/`mvn_log_prob`/
+// `mvn_sample` (src/liesel/goose/iwls_utils.py:14-70) and `beta @ K @ beta`
+// (src/liesel/model/distreg.py:291).
+#include "common.cuh"
+#include "prologue.cuh"
+
+namespace lslb {
+
+enum { TK_SPLINE = 0, TK_INTERCEPT = 1, TK_DENSE = 2 };
+
+struct IwlsParams {
+  int tkind;   // TK_*
+  int tidx;    // index within ep.sp / ep.dn / ep.ic
+  int p;       // coefficients of the target block
+  int tpred;
+  int nq;      // accumulator rows per chunk
+  void* partial;  // [nchunks][nq][Cpad]
+};
+
+// accumulator rows: score [p] then
+//   spline    : band [p][4]  entry (a, a+d) at p + 4a + d
+//   dense     : packed upper triangle, (a<=b) at p + a*p - a(a-1)/2 + (b-a)
+//   intercept : single entry at 1
+__host__ __device__ inline int iwls_nq(int tkind, int p) {
+  if (tkind == TK_SPLINE) return p + 4 * p;
+  if (tkind == TK_INTERCEPT) return 2;
+  return p + p * (p + 1) / 2;
+}
+
+template <typename T, int FAM, int NS, bool GROUP>
+__global__ void __launch_bounds__(128)
+iwls_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ IwlsParams q,
+            int fstride) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int TC = blockDim.x, tid = threadIdx.x;
+  const int c = blockIdx.y * TC + tid;
+  T* bs = reinterpret_cast<T*>(smraw);
+  T* as = bs + (size_t)p.Psmall * TC;  // accumulators [nq][TC]
+
+  for (int j = 0; j < p.Psmall; ++j) bs[j * TC + tid] = p.pT[(size_t)j * p.Cpad + c];
+  for (int j = 0; j < q.nq; ++j) as[j * TC + tid] = T(0);
+
+  int f0 = blockIdx.x * fstride;
+  int f1 = min(f0 + fstride, p.nchunks);
+  const long long r0 = p.chunk_start[f0], r1 = p.chunk_start[f1];
+
+  T o0 = T(0), o1 = T(0);
+  for (int k = 0; k < p.ni; ++k) {
+    T v = bs[p.ic[k].soff * TC + tid];
+    if (p.ic[k].pred) o1 += v; else o0 += v;
+  }
+  int cur[NS > 0 ? NS : 1];
+  T wb[NS > 0 ? NS : 1][4];
+#pragma unroll
+  for (int m = 0; m < NS; ++m) {
+    cur[m] = -1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) wb[m][t] = T(0);
+  }
+  // target-spline working set: score[4] + upper triangle of the 4x4 outer product
+  int tcur = -1;
+  T ts[4] = {T(0), T(0), T(0), T(0)};
+  T tg[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) tg[t] = T(0);
+  T is = T(0), ig = T(0);  // intercept target
+  int curg = -1;
+  T bg = T(0);
+
+  auto flush_target = [&]() {
+    if (tcur < 0) return;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) as[(tcur + a) * TC + tid] += ts[a];
+    int u = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a; b < 4; ++b) {
+        as[(q.p + 4 * (tcur + a) + (b - a)) * TC + tid] += tg[u];
+        ++u;
+      }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ts[a] = T(0);
+#pragma unroll
+    for (int t = 0; t < 10; ++t) tg[t] = T(0);
+  };
+
+  for (long long i = r0; i < r1; ++i) {
+    T eta0 = o0, eta1 = o1;
+    Vec4<T> wt = {T(0), T(0), T(0), T(0)};
+    int st = 0;
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      if (m < p.ns) {
+        const int s = __ldg(p.sp[m].start + i);
+        Vec4<T> w = ld4(p.sp[m].w + 4 * i);
+        if (s != cur[m]) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) wb[m][t] = bs[(p.sp[m].soff + s + t) * TC + tid];
+          cur[m] = s;
+        }
+        T v = w.a * wb[m][0];
+        v = fma(w.b, wb[m][1], v);
+        v = fma(w.c, wb[m][2], v);
+        v = fma(w.d, wb[m][3], v);
+        if (p.sp[m].pred) eta1 += v; else eta0 += v;
+        if (q.tkind == TK_SPLINE && m == q.tidx) {
+          wt = w;
+          st = s;
+        }
+      }
+    }
+    for (int d = 0; d < p.nd; ++d) {
+      const T* xrow = p.dn[d].X + i * p.dn[d].ld;
+      const T* bcol = bs + (size_t)p.dn[d].soff * TC + tid;
+      T v = T(0);
+      for (int j = 0; j < p.dn[d].p; ++j) v = fma(__ldg(xrow + j), bcol[j * TC], v);
+      if (p.dn[d].pred) eta1 += v; else eta0 += v;
+    }
+    if constexpr (GROUP) {
+      const int g = __ldg(p.gidx + i);
+      if (g != curg) {
+        curg = g;
+        bg = p.bT[(size_t)g * p.Cpad + c];
+      }
+      if (p.gpred) eta1 += bg; else eta0 += bg;
+    }
+    T ll, d0, d1, u0, u1;
+    lik_row<T, FAM, true>(__ldg(p.y + i), eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+    const T r = q.tpred ? d1 : d0;
+    const T W = q.tpred ? u1 : u0;
+
+    if (q.tkind == TK_SPLINE) {
+      if (st != tcur) {
+        flush_target();
+        tcur = st;
+      }
+      const T wv[4] = {wt.a, wt.b, wt.c, wt.d};
+      int u = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        ts[a] = fma(wv[a], r, ts[a]);
+        const T wa = wv[a] * W;
+#pragma unroll
+        for (int b = a; b < 4; ++b) {
+          tg[u] = fma(wa, wv[b], tg[u]);
+          ++u;
+        }
+      }
+    } else if (q.tkind == TK_INTERCEPT) {
+      is += r;
+      ig += W;
+    } else {
+      const DnsP<T>& D = p.dn[q.tidx];
+      const T* xrow = D.X + i * D.ld;
+      T* tri = as + (size_t)q.p * TC + tid;
+      for (int a = 0; a < q.p; ++a) {
+        const T xa = __ldg(xrow + a);
+        as[a * TC + tid] = fma(xa, r, as[a * TC + tid]);
+        const T xw = xa * W;
+        for (int b = a; b < q.p; ++b) {
+          tri[0] = fma(xw, __ldg(xrow + b), tri[0]);
+          tri += TC;
+        }
+      }
+    }
+  }
+  if (q.tkind == TK_SPLINE) flush_target();
+  if (q.tkind == TK_INTERCEPT) {
+    as[tid] = is;
+    as[TC + tid] = ig;
+  }
+  T* out = reinterpret_cast<T*>(q.partial) + (size_t)blockIdx.x * q.nq * p.Cpad + c;
+  for (int j = 0; j < q.nq; ++j) out[(size_t)j * p.Cpad] = as[j * TC + tid];
+}
+
+// score [C x p], info [C x p x p] from the chunk partials + prior terms
+template <typename T>
+__global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, int block, int tkind,
+                                     int p, int nq, const T* __restrict__ partial,
+                                     const T* __restrict__ pT, const T* __restrict__ aux,
+                                     T* __restrict__ score, T* __restrict__ info) {
+  // thread per (entry e in [0, p + p*p), chain c); c fastest for coalesced partial reads
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ne = p + p * p;
+  if (idx >= (long long)ne * fp.Cpad) return;
+  const int c = (int)(idx % fp.Cpad);
+  const int e = (int)(idx / fp.Cpad);
+  if (c >= fp.C) return;
+  const PriorP& pr = fp.pr[block];
+  const bool with_prior = !(fp.flags & LSLB_SKIP_PRIOR);
+  double tau2 = 1.0;
+  if (pr.prior == LSLB_PRIOR_MVND)
+    tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)c * fp.A + pr.tau2_slot] : pr.tau2_fixed;
+  const size_t stride = (size_t)nq * fp.Cpad;
+  if (e < p) {
+    double acc = 0.0;
+    const T* src = partial + (size_t)e * fp.Cpad + c;
+    for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+    if (with_prior) {
+      if (pr.prior == LSLB_PRIOR_NORMAL) {
+        acc -= ((double)pT[(size_t)(pr.soff + e) * fp.Cpad + c] - pr.m) * pr.inv_s2;
+      } else if (pr.prior == LSLB_PRIOR_MVND) {
+        const T* K = reinterpret_cast<const T*>(pr.K) + (size_t)e * p;
+        double kb = 0.0;
+        for (int i = 0; i < p; ++i) kb += (double)K[i] * (double)pT[(size_t)(pr.soff + i) * fp.Cpad + c];
+        acc -= kb / tau2;
+      }
+    }
+    score[(size_t)c * p + e] = (T)acc;
+    return;
+  }
+  const int a0 = (e - p) / p, b0 = (e - p) % p;
+  const int a = a0 < b0 ? a0 : b0, b = a0 < b0 ? b0 : a0;
+  double acc = 0.0;
+  int row = -1;
+  if (tkind == TK_SPLINE) {
+    if (b - a < 4) row = p + 4 * a + (b - a);
+  } else if (tkind == TK_INTERCEPT) {
+    row = 1;
+  } else {
+    row = p + a * p - a * (a - 1) / 2 + (b - a);
+  }
+  if (row >= 0) {
+    const T* src = partial + (size_t)row * fp.Cpad + c;
+    for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+  }
+  if (with_prior) {
+    if (pr.prior == LSLB_PRIOR_NORMAL) {
+      if (a == b) acc += pr.inv_s2;
+    } else if (pr.prior == LSLB_PRIOR_MVND) {
+      acc += (double)reinterpret_cast<const T*>(pr.K)[(size_t)a0 * p + b0] / tau2;
+    }
+  }
+  info[((size_t)c * p + a0) * p + b0] = (T)acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// ridge + Cholesky: one warp per chain, matrix staged in shared memory
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void chol_kernel(int C, int p, const T* __restrict__ info, T* __restrict__ chol) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const int ld = p + 1;
+  T* a = reinterpret_cast<T*>(smraw) + (size_t)warp * p * ld;
+  const T* src = info + (size_t)c * p * p;
+  bool finite = true;
+  T tr = T(0);
+  for (int e = lane; e < p * p; e += 32) {
+    T v = src[e];
+    a[(e / p) * ld + (e % p)] = v;
+    if (!isfinite(v)) finite = false;
+  }
+  __syncwarp();
+  for (int j = 0; j < p; ++j) tr += a[j * ld + j];  // same order on every lane
+  const T ridge = T(1e-6) * (tr / T(p));           // iwls.py:233-237
+  __syncwarp();
+  if (lane == 0)
+    for (int j = 0; j < p; ++j) a[j * ld + j] += ridge;
+  __syncwarp();
+  bool ok = __all_sync(0xffffffffu, finite);
+  for (int j = 0; j < p && ok; ++j) {
+    T d = a[j * ld + j];
+    if (!(d > T(0)) || !isfinite(d)) {
+      ok = false;
+      break;
+    }
+    d = sqrt(d);
+    const T inv = T(1) / d;
+    __syncwarp();
+    for (int i = j + lane; i < p; i += 32) a[i * ld + j] = (i == j) ? d : a[i * ld + j] * inv;
+    __syncwarp();
+    for (int i = j + 1 + lane; i < p; i += 32) {
+      const T lij = a[i * ld + j];
+      for (int k = j + 1; k <= i; ++k) a[i * ld + k] -= lij * a[k * ld + j];
+    }
+    __syncwarp();
+  }
+  T* dst = chol + (size_t)c * p * p;
+  const T nanv = (T)NAN;
+  for (int e = lane; e < p * p; e += 32) {
+    int i = e / p, k = e % p;
+    dst[e] = ok ? (k <= i ? a[i * ld + k] : T(0)) : nanv;
+  }
+}
+
+template <typename T>
+int launch_chol(int C, int p, const T* info, T* chol, cudaStream_t stream) {
+  if (C < 1 || p < 1 || p > LSLB_MAX_IWLS_P || !info || !chol) return LSLB_ERR_INVALID;
+  int wpb = 4;
+  size_t smem = (size_t)wpb * p * (p + 1) * sizeof(T);
+  auto kern = chol_kernel<T>;
+  if (smem > 48 * 1024)
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(C + wpb - 1) / wpb, wpb * 32, smem, stream>>>(C, p, info, chol);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+template int launch_chol<float>(int, int, const float*, float*, cudaStream_t);
+template int launch_chol<double>(int, int, const double*, double*, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------
+// proposal tail: one warp per chain
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void propose_kernel(int C, int p, const T* __restrict__ beta, const T* __restrict__ score,
+                               const T* __restrict__ chol, const T* __restrict__ step,
+                               const T* __restrict__ z, const T* __restrict__ x_eval,
+                               T* __restrict__ prop, T* __restrict__ logq) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (c >= C) return;
+  const int ld = p + 1;
+  T* L = reinterpret_cast<T*>(smraw) + (size_t)warp * (p * ld + 3 * p);
+  T* v = L + p * ld;   // work vector
+  T* mu = v + p;
+  T* u = mu + p;
+  const T* Lc = chol + (size_t)c * p * p;
+  for (int e = lane; e < p * p; e += 32) L[(e / p) * ld + (e % p)] = Lc[e];
+  for (int j = lane; j < p; j += 32) v[j] = score[(size_t)c * p + j];
+  __syncwarp();
+  // forward substitution L y = score (iwls_utils.py:27)
+  for (int j = 0; j < p; ++j) {
+    const T yj = v[j] / L[j * ld + j];
+    __syncwarp();
+    if (lane == 0) v[j] = yj;
+    for (int i = j + 1 + lane; i < p; i += 32) v[i] -= L[i * ld + j] * yj;
+    __syncwarp();
+  }
+  // backward substitution L^T x = y (iwls_utils.py:28)
+  for (int j = p - 1; j >= 0; --j) {
+    const T xj = v[j] / L[j * ld + j];
+    __syncwarp();
+    if (lane == 0) v[j] = xj;
+    for (int i = lane; i < j; i += 32) v[i] -= L[j * ld + i] * xj;
+    __syncwarp();
+  }
+  const T st = step[c];
+  const T half_s2 = st * st * T(0.5);
+  for (int j = lane; j < p; j += 32) mu[j] = beta[(size_t)c * p + j] + half_s2 * v[j];
+  __syncwarp();
+  if (z != nullptr) {
+    // prop = mu + (L/step)^{-T} z = mu + step * L^{-T} z   (iwls_utils.py:68-70)
+    for (int j = lane; j < p; j += 32) v[j] = z[(size_t)c * p + j];
+    __syncwarp();
+    for (int j = p - 1; j >= 0; --j) {
+      const T xj = v[j] / L[j * ld + j];
+      __syncwarp();
+      if (lane == 0) v[j] = xj;
+      for (int i = lane; i < j; i += 32) v[i] -= L[j * ld + i] * xj;
+      __syncwarp();
+    }
+    for (int j = lane; j < p; j += 32) {
+      const T x = mu[j] + st * v[j];
+      u[j] = x;
+      prop[(size_t)c * p + j] = x;
+    }
+  } else {
+    for (int j = lane; j < p; j += 32) u[j] = x_eval[(size_t)c * p + j];
+  }
+  __syncwarp();
+  // log q = sum_j [-0.5 s_j^2 - 0.5 log 2pi] + sum_j log(L_jj / step),  s = (x - mu) @ (L/step)
+  const T half_log_2pi = T(0.91893853320467274178);
+  T acc = T(0);
+  for (int j = lane; j < p; j += 32) {
+    T s = T(0);
+    for (int i = j; i < p; ++i) s += (u[i] - mu[i]) * L[i * ld + j];
+    s /= st;
+    acc += T(-0.5) * s * s - half_log_2pi + log(L[j * ld + j] / st);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) logq[c] = acc;
+}
+
+template <typename T>
+int launch_propose(int C, int p, const T* beta, const T* score, const T* chol, const T* step,
+                   const T* z, const T* x_eval, T* prop, T* logq, cudaStream_t stream) {
+  if (C < 1 || p < 1 || p > LSLB_MAX_IWLS_P || !beta || !score || !chol || !step || !logq)
+    return LSLB_ERR_INVALID;
+  if ((z == nullptr) == (x_eval == nullptr)) return LSLB_ERR_INVALID;
+  if (z != nullptr && !prop) return LSLB_ERR_INVALID;
+  int wpb = 4;
+  size_t smem = (size_t)wpb * (p * (p + 1) + 3 * p) * sizeof(T);
+  auto kern = propose_kernel<T>;
+  if (smem > 48 * 1024)
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(C + wpb - 1) / wpb, wpb * 32, smem, stream>>>(C, p, beta, score, chol, step, z, x_eval,
+                                                        prop, logq);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// beta^T K beta
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void quadform_kernel(int C, int P, int off, int k, const T* __restrict__ params,
+                                const T* __restrict__ K, T* __restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const T* b = params + (size_t)c * P + off;
+  double q = 0.0;
+  for (int j = 0; j < k; ++j) {
+    double xk = 0.0;
+    for (int i = 0; i < k; ++i) xk += (double)b[i] * (double)K[(size_t)i * k + j];
+    q += xk * (double)b[j];
+  }
+  out[c] = (T)q;
+}
+
+template <typename T>
+int launch_quadform(const lslb_plan* plan, int C, int block, const T* params, T* out,
+                    cudaStream_t stream) {
+  if (!plan || C < 1 || block < 0 || block >= plan->desc.nblocks || !params || !out)
+    return LSLB_ERR_INVALID;
+  if ((plan->desc.dtype == LSLB_F32) != (sizeof(T) == 4)) return LSLB_ERR_INVALID;
+  const lslb_block_desc& d = plan->blk[block];
+  if (d.prior != LSLB_PRIOR_MVND) return LSLB_ERR_INVALID;
+  quadform_kernel<T><<<(C + 127) / 128, 128, 0, stream>>>(C, plan->P, plan->off[block], d.ncoef,
+                                                          params, reinterpret_cast<const T*>(d.K), out);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side of the IWLS pass
+// ---------------------------------------------------------------------------------------
+static bool iwls_target(const lslb_plan* plan, int block, int& tkind, int& tidx) {
+  if (block < 0 || block >= plan->desc.nblocks) return false;
+  for (int m = 0; m < plan->ns; ++m)
+    if (plan->sp[m] == block) { tkind = TK_SPLINE; tidx = m; return true; }
+  for (int m = 0; m < plan->ni; ++m)
+    if (plan->ic[m] == block) { tkind = TK_INTERCEPT; tidx = m; return true; }
+  for (int m = 0; m < plan->nd; ++m)
+    if (plan->dn[m] == block) { tkind = TK_DENSE; tidx = m; return true; }
+  return false;  // group blocks: a G x G information matrix is not materialised
+}
+
+static size_t iwls_smem_per_chain(const lslb_plan* plan, int nq) {
+  return (size_t)(plan->Psmall + nq) * (plan->desc.dtype == LSLB_F32 ? 4 : 8);
+}
+
+template <typename T>
+struct IwlsWs {
+  T *pT, *partial, *bT, *gbT, *gpl;
+  size_t bytes;
+};
+
+template <typename T>
+static IwlsWs<T> iwls_layout(const lslb_plan* plan, const LaunchCfg& k, int nq, void* ws) {
+  IwlsWs<T> L;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    T* ptr = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+    off += align_up(n * sizeof(T), 256);
+    return ptr;
+  };
+  L.pT = take((size_t)plan->Psmall * k.Cpad);
+  L.partial = take((size_t)k.nchunks * nq * k.Cpad);
+  L.bT = L.gbT = L.gpl = nullptr;
+  if (plan->grp >= 0) {
+    int G = plan->blk[plan->grp].ncoef;
+    L.bT = take((size_t)G * k.Cpad);
+    L.gbT = take((size_t)G * k.Cpad);
+    L.gpl = take((size_t)((G + 31) / 32) * k.Cpad);
+  }
+  L.bytes = off;
+  return L;
+}
+
+size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
+  size_t best = 0;
+  for (int b = 0; b < plan->desc.nblocks; ++b) {
+    int tkind, tidx;
+    if (!iwls_target(plan, b, tkind, tidx)) continue;
+    int p = plan->blk[b].ncoef;
+    if (p > LSLB_MAX_IWLS_P) continue;
+    int nq = iwls_nq(tkind, p);
+    LaunchCfg k = choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+    size_t bytes = plan->desc.dtype == LSLB_F32 ? iwls_layout<float>(plan, k, nq, nullptr).bytes
+                                                : iwls_layout<double>(plan, k, nq, nullptr).bytes;
+    if (bytes > best) best = bytes;
+  }
+  return best;
+}
+
+template <typename T, int FAM>
+static int iwls_dispatch(const lslb_plan* plan, const EvalParams<T>& ep, const IwlsParams& q,
+                         const LaunchCfg& k, size_t smem, cudaStream_t st) {
+  dim3 grid(k.nchunks, k.ntiles), block(k.TC);
+#define LSLB_IWLS_LAUNCH(NS, GRP)                                                              \
+  do {                                                                                         \
+    auto kern = iwls_kernel<T, FAM, NS, GRP>;                                                  \
+    if (smem > 48 * 1024)                                                                      \
+      LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, block, smem, st>>>(ep, q, k.fstride);                                         \
+  } while (0)
+  if (plan->grp >= 0) LSLB_IWLS_LAUNCH(8, true);
+  else if (plan->ns <= 2) LSLB_IWLS_LAUNCH(2, false);
+  else LSLB_IWLS_LAUNCH(8, false);
+#undef LSLB_IWLS_LAUNCH
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
+template <typename T>
+int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const T* aux, T* score,
+                T* info, T* chol, unsigned flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (!plan || C < 1 || !params || !score || !info || !ws) return LSLB_ERR_INVALID;
+  if (plan->A > 0 && !aux) return LSLB_ERR_INVALID;
+  if ((plan->desc.dtype == LSLB_F32) != (sizeof(T) == 4)) return LSLB_ERR_INVALID;
+  int tkind, tidx;
+  if (!iwls_target(plan, block, tkind, tidx)) return LSLB_ERR_UNSUPPORTED;
+  const int p = plan->blk[block].ncoef;
+  if (p > LSLB_MAX_IWLS_P) return LSLB_ERR_UNSUPPORTED;
+  const int nq = iwls_nq(tkind, p);
+  LaunchCfg k = choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+  size_t smem = iwls_smem_per_chain(plan, nq) * k.TC;
+  if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
+  IwlsWs<T> L = iwls_layout<T>(plan, k, nq, ws);
+  if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
+
+  FinalizeParams fp;
+  fill_finalize_params(plan, fp, C, k.Cpad, k.nchunks, flags);
+  EvalParams<T> ep;
+  fill_eval_params<T>(plan, ep, C, k.Cpad);
+  ep.pT = L.pT;
+  ep.partial = nullptr;
+  ep.bT = L.bT;
+  ep.gbT = L.gbT;
+  IwlsParams q;
+  q.tkind = tkind;
+  q.tidx = tidx;
+  q.p = p;
+  q.tpred = plan->blk[block].predictor;
+  q.nq = nq;
+  q.partial = L.partial;
+
+  long long total = (long long)plan->Psmall * k.Cpad;
+  gather_small_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fp, params, L.pT);
+  LSLB_LAUNCH_CHECK();
+  if (plan->grp >= 0) {
+    const lslb_block_desc& d = plan->blk[plan->grp];
+    dim3 grid((d.ncoef + 31) / 32, (k.Cpad + 31) / 32), blockd(32, 8);
+    group_init_kernel<T><<<grid, blockd, 0, stream>>>(params, plan->P, plan->off[plan->grp], d.ncoef,
+                                                      C, k.Cpad, (T)d.prior_m, T(0), false, L.bT,
+                                                      L.gbT, L.gpl);
+    LSLB_LAUNCH_CHECK();
+  }
+  int st = LSLB_ERR_INVALID;
+  switch (plan->fam) {
+    case FAM_NORMAL_LS: st = iwls_dispatch<T, FAM_NORMAL_LS>(plan, ep, q, k, smem, stream); break;
+    case FAM_NORMAL_FIXED: st = iwls_dispatch<T, FAM_NORMAL_FIXED>(plan, ep, q, k, smem, stream); break;
+    case FAM_BERNOULLI: st = iwls_dispatch<T, FAM_BERNOULLI>(plan, ep, q, k, smem, stream); break;
+    case FAM_POISSON: st = iwls_dispatch<T, FAM_POISSON>(plan, ep, q, k, smem, stream); break;
+  }
+  if (st != LSLB_OK) return st;
+  long long ne = (long long)(p + p * p) * k.Cpad;
+  iwls_finalize_kernel<T><<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(
+      fp, block, tkind, p, nq, L.partial, L.pT, aux, score, info);
+  LSLB_LAUNCH_CHECK();
+  if (chol) return launch_chol<T>(C, p, info, chol, stream);
+  return LSLB_OK;
+}
+template int launch_iwls<float>(const lslb_plan*, int, int, const float*, const float*, float*,
+                                float*, float*, unsigned, void*, size_t, cudaStream_t);
+template int launch_iwls<double>(const lslb_plan*, int, int, const double*, const double*, double*,
+                                 double*, double*, unsigned, void*, size_t, cudaStream_t);
+
+}  // namespace lslb
+
+#define LSLB_S(x) ((cudaStream_t)(x))
+extern "C" int lslb_iwls_f32(const lslb_plan* plan, int C, int block, const float* params,
+                             const float* aux, float* score, float* info, float* chol,
+                             uint32_t flags, void* ws, size_t ws_bytes, lslb_stream_t s) {
+  return lslb::launch_iwls<float>(plan, C, block, params, aux, score, info, chol, flags, ws, ws_bytes, LSLB_S(s));
+}
+extern "C" int lslb_iwls_f64(const lslb_plan* plan, int C, int block, const double* params,
+                             const double* aux, double* score, double* info, double* chol,
+                             uint32_t flags, void* ws, size_t ws_bytes, lslb_stream_t s) {
+  return lslb::launch_iwls<double>(plan, C, block, params, aux, score, info, chol, flags, ws, ws_bytes, LSLB_S(s));
+}
+extern "C" int lslb_chol_f32(int C, int p, const float* info, float* chol, lslb_stream_t s) {
+  return lslb::launch_chol<float>(C, p, info, chol, LSLB_S(s));
+}
+extern "C" int lslb_chol_f64(int C, int p, const double* info, double* chol, lslb_stream_t s) {
+  return lslb::launch_chol<double>(C, p, info, chol, LSLB_S(s));
+}
+extern "C" int lslb_quadform_f32(const lslb_plan* plan, int C, int block, const float* params,
+                                 float* out, lslb_stream_t s) {
+  return lslb::launch_quadform<float>(plan, C, block, params, out, LSLB_S(s));
+}
+extern "C" int lslb_quadform_f64(const lslb_plan* plan, int C, int block, const double* params,
+                                 double* out, lslb_stream_t s) {
+  return lslb::launch_quadform<double>(plan, C, block, params, out, LSLB_S(s));
+}
+extern "C" int lslb_iwls_propose_f32(int C, int p, const float* beta, const float* score,
+                                     const float* chol, const float* step, const float* z,
+                                     const float* x_eval, float* prop, float* logq,
+                                     lslb_stream_t s) {
+  return lslb::launch_propose<float>(C, p, beta, score, chol, step, z, x_eval, prop, logq, LSLB_S(s));
+}
+extern "C" int lslb_iwls_propose_f64(int C, int p, const double* beta, const double* score,
+                                     const double* chol, const double* step, const double* z,
+                                     const double* x_eval, double* prop, double* logq,
+                                     lslb_stream_t s) {
+  return lslb::launch_propose<double>(C, p, beta, score, chol, step, z, x_eval, prop, logq, LSLB_S(s));
+}

@@ -1,0 +1,212 @@
+// Plan construction: validates the model description, fixes the parameter layout, derives
+// the row chunking (aligned to group boundaries when a random intercept is present) and the
+// row-independent likelihood constant. Setup-time code: synchronous by design.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace lslb {
+
+static thread_local char g_err[256] = "";
+void set_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+}
+
+// fine chunk boundaries: fine[f] = f*n/F moved forward to the next group start
+__global__ void fine_bounds_kernel(long long n, int F, const int* __restrict__ gidx,
+                                   long long* __restrict__ fine) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > F) return;
+  long long r = (f == F) ? n : (long long)((double)f * (double)n / (double)F);
+  if (r > n) r = n;
+  if (gidx != nullptr && f != 0 && f != F) {
+    while (r < n && r > 0 && gidx[r] == gidx[r - 1]) ++r;
+  }
+  fine[f] = r;
+}
+
+// sum_i lgamma(y_i + 1) in double, one block, fixed order (deterministic)
+template <typename T>
+__global__ void lgamma_sum_kernel(const T* __restrict__ y, long long n, double* out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += lgamma((double)y[i] + 1.0);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+}  // namespace lslb
+
+using namespace lslb;
+
+extern "C" int lslb_version(void) { return LSLB_VERSION; }
+
+extern "C" const char* lslb_status_string(int s) {
+  switch (s) {
+    case LSLB_OK: return "ok";
+    case LSLB_ERR_INVALID: return "invalid argument or unsupported model structure";
+    case LSLB_ERR_WORKSPACE: return "workspace too small";
+    case LSLB_ERR_CUDA: return "CUDA runtime error";
+    case LSLB_ERR_UNSUPPORTED: return "not implemented for this configuration";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* lslb_last_cuda_error(void) { return g_err; }
+
+extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
+  if (!desc || !out) return LSLB_ERR_INVALID;
+  *out = nullptr;
+  if (desc->nblocks < 1 || desc->nblocks > LSLB_MAX_BLOCKS || desc->n < 0 || !desc->blocks)
+    return LSLB_ERR_INVALID;
+  if (desc->dtype != LSLB_F32 && desc->dtype != LSLB_F64) return LSLB_ERR_INVALID;
+  if (desc->family < LSLB_NORMAL || desc->family > LSLB_POISSON) return LSLB_ERR_INVALID;
+  if (desc->n > 0 && !desc->y) return LSLB_ERR_INVALID;
+
+  lslb_plan* p = new (std::nothrow) lslb_plan();
+  if (!p) return LSLB_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->desc = *desc;
+  p->grp = -1;
+  int off = 0, soff = 0, aux = 0;
+  for (int b = 0; b < desc->nblocks; ++b) {
+    const lslb_block_desc& d = desc->blocks[b];
+    p->blk[b] = d;
+    bool bad = d.ncoef < 1 || d.predictor < 0 || d.predictor > 1 ||
+               (d.predictor == 1 && desc->family != LSLB_NORMAL) || d.prior < LSLB_PRIOR_NONE ||
+               d.prior > LSLB_PRIOR_MVND;
+    if (d.prior == LSLB_PRIOR_MVND && (!d.K || d.kind == LSLB_GROUP)) bad = true;
+    if (d.prior == LSLB_PRIOR_NORMAL && !(d.prior_s > 0)) bad = true;
+    switch (d.kind) {
+      case LSLB_DENSE:
+        if (!d.data || d.ld < d.ncoef || p->nd >= LSLB_MAX_DNS) bad = true;
+        else p->dn[p->nd++] = b;
+        break;
+      case LSLB_SPLINE:
+        if (!d.data || !d.index || d.ncoef < 4 || p->ns >= LSLB_MAX_SPL) bad = true;
+        else p->sp[p->ns++] = b;
+        break;
+      case LSLB_GROUP:
+        if (!d.index || p->grp >= 0) bad = true;
+        else p->grp = b;
+        break;
+      case LSLB_INTERCEPT:
+        if (d.ncoef != 1 || p->ni >= LSLB_MAX_INT) bad = true;
+        else p->ic[p->ni++] = b;
+        break;
+      default: bad = true;
+    }
+    if (bad) {
+      delete p;
+      return LSLB_ERR_INVALID;
+    }
+    p->off[b] = off;
+    off += d.ncoef;
+    if (d.kind == LSLB_GROUP) {
+      p->soff[b] = -1;
+    } else {
+      p->soff[b] = soff;
+      soff += d.ncoef;
+    }
+    if (d.prior == LSLB_PRIOR_MVND && d.tau2_slot >= 0) aux = aux > d.tau2_slot + 1 ? aux : d.tau2_slot + 1;
+    if (d.predictor == 1) p->has_scale = true;
+  }
+  p->desc.blocks = p->blk;
+  p->P = off;
+  p->Psmall = soff;
+  p->A = aux;
+  p->fam = desc->family == LSLB_NORMAL ? (p->has_scale ? FAM_NORMAL_LS : FAM_NORMAL_FIXED)
+                                       : desc->family;
+  if (p->fam == FAM_NORMAL_FIXED && !(desc->fixed_scale > 0)) {
+    delete p;
+    return LSLB_ERR_INVALID;
+  }
+
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "device query");
+    delete p;
+    return LSLB_ERR_CUDA;
+  }
+
+  // fine chunking: at most 16 chunks per SM, at least 32 rows per chunk
+  long long n = desc->n;
+  long long F = (long long)p->sm_count * 16;
+  if (F > (n + 31) / 32) F = (n + 31) / 32;
+  if (F < 1) F = 1;
+  p->nchunks = (int)F;
+  e = cudaMalloc(&p->d_chunk_start, sizeof(long long) * (F + 1));
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "cudaMalloc(chunk_start)");
+    delete p;
+    return LSLB_ERR_CUDA;
+  }
+  const int* gidx = p->grp >= 0 ? p->blk[p->grp].index : nullptr;
+  fine_bounds_kernel<<<(unsigned)((F + 1 + 255) / 256), 256>>>(n, (int)F, gidx, p->d_chunk_start);
+
+  // row-independent likelihood constant
+  const double half_log_2pi = 0.91893853320467274178;
+  p->lik_const = 0.0;
+  if (desc->family == LSLB_NORMAL) {
+    p->lik_const = -half_log_2pi * (double)n;
+    if (p->fam == FAM_NORMAL_FIXED) p->lik_const -= log(desc->fixed_scale) * (double)n;
+  } else if (desc->family == LSLB_POISSON && n > 0) {
+    double* d_out = nullptr;
+    e = cudaMalloc(&d_out, sizeof(double));
+    if (e == cudaSuccess) {
+      if (desc->dtype == LSLB_F32)
+        lgamma_sum_kernel<float><<<1, 1024>>>((const float*)desc->y, n, d_out);
+      else
+        lgamma_sum_kernel<double><<<1, 1024>>>((const double*)desc->y, n, d_out);
+      double h = 0.0;
+      e = cudaMemcpy(&h, d_out, sizeof(double), cudaMemcpyDeviceToHost);
+      p->lik_const = -h;
+      cudaFree(d_out);
+    }
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "plan setup kernels");
+    cudaFree(p->d_chunk_start);
+    delete p;
+    return LSLB_ERR_CUDA;
+  }
+
+  // kernel variant
+  if (p->grp < 0 && p->nd == 0 && p->ns >= 1) {
+    p->variant = VAR_BANDED;
+    p->variant_name = "banded_runlength";
+  } else if (p->ns == 0 && p->nd == 1 && p->blk[p->dn[0]].ncoef <= 16) {
+    p->variant = VAR_DENSE_REG;
+    p->variant_name = "dense_registers";
+  } else {
+    p->variant = VAR_GENERIC;
+    p->variant_name = "generic_smem";
+  }
+  *out = p;
+  return LSLB_OK;
+}
+
+extern "C" void lslb_plan_destroy(lslb_plan* p) {
+  if (!p) return;
+  if (p->d_chunk_start) cudaFree(p->d_chunk_start);
+  delete p;
+}
+
+extern "C" int lslb_plan_num_params(const lslb_plan* p) { return p ? p->P : -1; }
+extern "C" int lslb_plan_num_aux(const lslb_plan* p) { return p ? p->A : -1; }
+extern "C" const char* lslb_plan_variant(const lslb_plan* p) { return p ? p->variant_name : ""; }
+extern "C" size_t lslb_workspace_bytes(const lslb_plan* p, int C) {
+  return p ? lslb::workspace_bytes(p, C) : 0;
+}

@@ -1,0 +1,71 @@
+// Prologue kernels shared by the logp/grad and IWLS passes (each TU instantiates its own copy).
+#pragma once
+#include "common.cuh"
+
+namespace lslb {
+
+// =======================================================================================
+// gather / scatter helpers
+// =======================================================================================
+template <typename T>
+__global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
+                                    const T* __restrict__ params, T* __restrict__ pT) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)fp.Psmall * fp.Cpad;
+  if (idx >= total) return;
+  int c = (int)(idx % fp.Cpad);
+  int j = (int)(idx / fp.Cpad);
+  T v = T(0);
+  if (c < fp.C) {
+    for (int b = 0; b < fp.nblocks; ++b) {
+      const PriorP& pr = fp.pr[b];
+      if (pr.soff >= 0 && j >= pr.soff && j < pr.soff + pr.ncoef) {
+        v = params[(long long)c * fp.P + pr.off + (j - pr.soff)];
+        break;
+      }
+    }
+  }
+  pT[idx] = v;
+}
+
+// params[:, goff:goff+G] ([C x G] view, row stride P)  ->  bT [G x Cpad]; also initialises the
+// gradient buffer with the prior gradient and emits per-tile prior log-density partials.
+template <typename T>
+__global__ void group_init_kernel(const T* __restrict__ params, int P, int goff, int G, int C,
+                                  int Cpad, T m, T inv_s2, bool with_prior, T* __restrict__ bT,
+                                  T* __restrict__ gbT, T* __restrict__ gpl) {
+  __shared__ T tile[32][33];
+  __shared__ T red[8][32];
+  int g0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int cl = ty + 8 * k;
+    int g = g0 + tx, c = c0 + cl;
+    tile[cl][tx] = (g < G && c < C) ? params[(long long)c * P + goff + g] : T(0);
+  }
+  __syncthreads();
+  T acc = T(0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int gl = ty + 8 * k;
+    int g = g0 + gl, c = c0 + tx;
+    if (g < G && c < Cpad) {
+      T b = tile[tx][gl];
+      bT[(long long)g * Cpad + c] = b;
+      T d = b - m;
+      gbT[(long long)g * Cpad + c] = with_prior ? -d * inv_s2 : T(0);
+      if (c < C) acc += T(-0.5) * d * d * inv_s2;
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c0 + tx < Cpad) {
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][tx];
+    gpl[(long long)blockIdx.x * Cpad + c0 + tx] = s;
+  }
+}
+
+}  // namespace lslb

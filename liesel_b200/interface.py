@@ -1,0 +1,121 @@
+"""
+``B200Interface`` — a ``ModelInterface`` (reference ``src/liesel/goose/types.py:72-102``)
+backed by the CUDA plan.
+
+The reference's protocol has three methods: ``extract_position(position_keys, model_state)``,
+``update_state(position, model_state)`` and ``log_prob(model_state)``. Its existing
+implementations are ``DictInterface`` (``goose/interface.py:19-112``, the state is a plain dict
+and ``update_state`` is ``model_state | position``, :101) and ``LieselInterface`` (:229-313,
+the state is every node of the graph). This class keeps a PARAMETER-ONLY state like
+``DictInterface`` — ``{name: array}`` for the coefficient vectors and the ``tau2`` values —
+while the data lives in the plan; ``log_prob`` calls the batched CUDA evaluation.
+
+Chain axis. Under the reference's engine every protocol method runs inside
+``jax.vmap`` over chains (``goose/engine.py:442-448``); JAX is not installed here, so the chain
+axis is explicit: every state leaf carries a leading dimension ``C`` and ``log_prob`` returns
+``[C]``. This is exactly the operand layout ``jax.ffi.ffi_call(..., vmap_method="broadcast_all")``
+hands to the C ABI.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from .plan import Plan
+
+Position = dict
+ModelState = dict
+
+
+class B200Interface:
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        spec = plan.spec
+        self._pos_keys = spec.position_keys()
+        self._aux_keys = spec.aux_keys()
+        self._slices = {
+            b.name + "_beta": slice(b.param_offset, b.param_offset + b.ncoef) for b in spec.blocks
+        }
+
+    # -- ModelInterface protocol (types.py:72-102) ------------------------------------
+    def extract_position(self, position_keys: Sequence[str], model_state: ModelState) -> Position:
+        """Same contract as ``DictInterface.extract_position`` (``interface.py:75-88``)."""
+        return Position({key: model_state[key] for key in position_keys})
+
+    def update_state(self, position: Position, model_state: ModelState) -> ModelState:
+        """``model_state | position`` (``interface.py:90-101``); evaluation is lazy."""
+        unknown = [k for k in position if k not in model_state]
+        if unknown:
+            raise KeyError(f"unknown position keys {unknown}")
+        return model_state | position
+
+    def log_prob(self, model_state: ModelState) -> torch.Tensor:
+        """Unnormalised log-posterior per chain, ``[C]`` (``interface.py:304-313``)."""
+        params, aux = self.pack(model_state)
+        logp, _ = self.plan.logp_grad(params, aux, want_grad=False)
+        return logp
+
+    # -- what jax.value_and_grad(log_prob_fn) yields in NUTS/HMC (nuts.py:193-194) ----
+    def log_prob_and_grad(self, model_state: ModelState, position_keys: Sequence[str] | None = None):
+        params, aux = self.pack(model_state)
+        logp, grad = self.plan.logp_grad(params, aux, want_grad=True)
+        keys = self._pos_keys if position_keys is None else list(position_keys)
+        bad = [k for k in keys if k not in self._slices]
+        if bad:
+            raise KeyError(f"no gradient available for {bad} (not a coefficient block)")
+        return logp, {k: grad[:, self._slices[k]] for k in keys}
+
+    # -- IWLSKernel(chol_info_fn=...) hook (iwls.py:130-145,241-243) ------------------
+    def chol_info_fn(self, position_key: str) -> Callable[[ModelState], torch.Tensor]:
+        block = self._block_of(position_key)
+
+        def fn(model_state: ModelState) -> torch.Tensor:
+            params, aux = self.pack(model_state)
+            _, _, chol = self.plan.iwls(block, params, aux, want_chol=True)
+            return chol
+
+        return fn
+
+    def score_and_info(self, position_key: str, model_state: ModelState, want_chol: bool = True):
+        params, aux = self.pack(model_state)
+        return self.plan.iwls(self._block_of(position_key), params, aux, want_chol=want_chol)
+
+    # -- state helpers -----------------------------------------------------------------
+    def initial_state(self, num_chains: int, position: dict | None = None) -> ModelState:
+        """
+        Replicated start state: zeros for coefficients (``distreg.py:101,165``) and the blocks'
+        ``tau2_init`` (reference default 10000.0, ``distreg.py:163``), overridable per key.
+        """
+        spec, dev, dt = self.plan.spec, self.plan.device, self.plan.dtype
+        state: ModelState = {}
+        for b in spec.blocks:
+            state[b.name + "_beta"] = torch.zeros((num_chains, b.ncoef), dtype=dt, device=dev)
+            if b.tau2_slot >= 0:
+                state[b.prior.tau2_name] = torch.full((num_chains,), b.prior.tau2_init, dtype=dt, device=dev)
+        for k, v in (position or {}).items():
+            if k not in state:
+                raise KeyError(k)
+            v = torch.as_tensor(v, dtype=dt, device=dev)
+            state[k] = v.expand(state[k].shape).contiguous() if v.dim() < state[k].dim() else v.contiguous()
+        return state
+
+    def pack(self, model_state: ModelState):
+        """State dict -> (params [C, P], aux [C, A]) in the plan's flat layout."""
+        params = torch.cat([model_state[k] for k in self._pos_keys], dim=1).contiguous()
+        aux = None
+        if self._aux_keys:
+            aux = torch.stack([model_state[k].reshape(-1) for k in self._aux_keys], dim=1).contiguous()
+        return params, aux
+
+    def unpack(self, params: torch.Tensor, aux: torch.Tensor | None = None) -> ModelState:
+        state = {k: params[:, s] for k, s in self._slices.items()}
+        for i, k in enumerate(self._aux_keys):
+            state[k] = aux[:, i]
+        return state
+
+    def _block_of(self, position_key: str) -> int:
+        if position_key not in self._slices:
+            raise KeyError(position_key)
+        return self._pos_keys.index(position_key)

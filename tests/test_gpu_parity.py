@@ -1,0 +1,339 @@
+"""
+Parity of the CUDA path (called through the C ABI via ctypes) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star: rtol 1e-5 fp32 / 1e-10 fp64 on log-prob, gradients and
+Gram; bit-exact basis and group indices):
+  * log-prob:  |err| <= rtol * |ref|
+  * gradient / information: |err| <= rtol * |ref| + ulps * eps * scale, where ``scale`` is the sum
+    of absolute values of the terms of that entry (oracle.sam.grad_scale) — entries that are a
+    near-cancelling sum of 1e5..1e6 terms cannot meet a pure relative bound in ANY float32
+    evaluation order, the reference's XLA reduction included.
+"""
+import numpy as np
+import pytest
+import torch
+
+from liesel_b200 import synth
+from oracle import iwls as OI
+from oracle import sam
+from oracle import splines as OS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-10}
+EPS = {np.dtype(np.float32): 2.0**-24, np.dtype(np.float64): 2.0**-53}
+ULPS = 16.0
+
+
+@pytest.fixture(scope="module")
+def lb():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from liesel_b200 import plan as P
+    from liesel_b200.interface import B200Interface
+
+    class NS:
+        Plan = P.Plan
+        chol = staticmethod(P.chol)
+        iwls_propose = staticmethod(P.iwls_propose)
+        Interface = B200Interface
+
+    return NS
+
+
+def make(cfg, dtype):
+    return {
+        "s1": lambda: synth.s1_blr(n=1000, dtype=dtype),
+        "s2": lambda: synth.s2_pspline_gam(n=20_000, dtype=dtype),
+        "s3": lambda: synth.s3_gamlss(n=50_000, dtype=dtype),
+        "s4": lambda: synth.s4_logistic(n=4000, p=48, dtype=dtype),
+        "s5": lambda: synth.s5_poisson_ri(n=20_000, G=500, dtype=dtype),
+        "s5u": lambda: synth.s5_poisson_ri(n=20_000, G=700, dtype=dtype, balanced=False),
+    }[cfg]()
+
+
+def dev(a, plan):
+    return torch.as_tensor(np.ascontiguousarray(a), device=plan.device)
+
+
+def check_logp_grad(spec, plan, th, aux, chains=None):
+    dt = np.dtype(spec.dtype)
+    logp, grad = plan.logp_grad(dev(th, plan), dev(aux, plan) if spec.num_aux else None)
+    logp_v, _ = plan.logp_grad(dev(th, plan), dev(aux, plan) if spec.num_aux else None, want_grad=False)
+    torch.cuda.synchronize()
+    logp, grad, logp_v = logp.cpu().numpy(), grad.cpu().numpy(), logp_v.cpu().numpy()
+    sel = np.arange(th.shape[0]) if chains is None else np.asarray(chains)
+    prep = sam.Prepared(spec)
+    ref_lp = sam.log_prob(spec, th[sel], aux[sel], prep=prep)
+    ref_g = sam.grad(spec, th[sel], aux[sel], prep=prep)
+    sc_g = sam.grad_scale(spec, th[sel], aux[sel], prep=prep)
+    sc_lp = sam.log_prob_scale(spec, th[sel], aux[sel], prep=prep)
+    # value-only and value+grad paths agree (mh_step reads log_prob without a gradient)
+    np.testing.assert_allclose(logp_v[sel], logp[sel], rtol=10 * EPS[dt])
+    err = np.abs(logp[sel] - ref_lp)
+    assert np.all(err <= RTOL[dt] * np.abs(ref_lp) + ULPS * EPS[dt] * sc_lp), (err.max(), ref_lp)
+    gerr = np.abs(grad[sel] - ref_g)
+    bound = RTOL[dt] * np.abs(ref_g) + ULPS * EPS[dt] * sc_g
+    assert np.all(gerr <= bound), float((gerr / bound).max())
+    return logp, grad
+
+
+@pytest.mark.parametrize("cfg", ["s1", "s2", "s3", "s4", "s5", "s5u"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_logp_grad_parity(lb, cfg, dtype):
+    spec, centre = make(cfg, dtype)
+    plan = lb.Plan(spec)
+    C = {"s1": 4, "s2": 64, "s3": 40, "s4": 12, "s5": 33, "s5u": 7}[cfg]
+    th, aux = synth.evaluation_points(spec, centre, C)
+    check_logp_grad(spec, plan, th, aux)
+
+
+@pytest.mark.parametrize("tau2", ["start", "loguniform"])
+def test_logp_grad_tau2_range(lb, tau2):
+    """tau2 spans 1e-3..1e4 during Gibbs sampling; also the reference's start state beta = 0."""
+    spec, centre = make("s3", np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 16, tau2=tau2)
+    if tau2 == "start":
+        th = np.zeros_like(th)  # distreg.py:101,165
+    check_logp_grad(spec, plan, th, aux)
+
+
+@pytest.mark.parametrize("C", [1, 3, 31, 33, 65, 130])
+def test_ragged_chain_counts(lb, C):
+    spec, centre = make("s3", np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, C)
+    check_logp_grad(spec, plan, th, aux)
+
+
+def test_unsorted_rows_same_result(lb):
+    """Row order is free: the span-sorted plan and the plan in data order agree."""
+    spec, centre = make("s2", np.float32)
+    th, aux = synth.evaluation_points(spec, centre, 8)
+    a = lb.Plan(spec, sort_rows=True)
+    b = lb.Plan(spec, sort_rows=False)
+    la, ga = check_logp_grad(spec, a, th, aux)
+    lb_, gb = check_logp_grad(spec, b, th, aux)
+    np.testing.assert_allclose(la, lb_, rtol=2e-6)
+
+
+def test_bitwise_reproducible(lb):
+    spec, centre = make("s3", np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 64)
+    t, a = dev(th, plan), dev(aux, plan)
+    l1, g1 = plan.logp_grad(t, a)
+    l1, g1 = l1.clone(), g1.clone()
+    l2, g2 = plan.logp_grad(t, a)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+
+
+def test_tiny_and_empty_inputs(lb):
+    for n in [1, 2, 31, 33]:
+        spec, centre = synth.s3_gamlss(n=max(n, 8), k=8, dtype=np.float64)
+        # cut to n rows
+        spec.y = spec.y[:n]
+        for b in spec.blocks:
+            if b.x is not None:
+                b.x = b.x[:n]
+        plan = lb.Plan(spec)
+        th, aux = synth.evaluation_points(spec, centre, 3)
+        check_logp_grad(spec, plan, th, aux)
+
+
+def test_nan_inf_propagate(lb):
+    """Numerical failure is signalled by NaN/Inf values, never by an exception (mh.py:53-57)."""
+    spec, centre = make("s5", np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 4)
+    th[1, 0] = 200.0  # exp overflow in the Poisson rate
+    th[2, 1] = np.nan
+    logp, grad = plan.logp_grad(dev(th, plan), None)
+    logp = logp.cpu().numpy()
+    assert np.isfinite(logp[0]) and np.isfinite(logp[3])
+    assert not np.isfinite(logp[1]) and np.isnan(logp[2])
+
+
+# --- spline basis -----------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_basis_bit_exact(lb, dtype):
+    from liesel_b200 import splines
+
+    rng = np.random.default_rng(3)
+    x = rng.uniform(size=200_000).astype(dtype)
+    knots = splines.equidistant_knots(x, 20, 3)
+    # adversarial points: every knot, and its neighbours one ulp away
+    edge = np.concatenate([knots, np.nextafter(knots, dtype(np.inf)), np.nextafter(knots, dtype(-np.inf))])
+    x = np.concatenate([x, edge.astype(dtype), [knots[0] - 1, knots[-1] + 1]]).astype(dtype)
+    start, w = splines.basis_matrix(x, knots, 3, outer_ok=True, device="cuda")
+    o_start, o_w = OS.banded_basis(x, knots, 3)
+    assert np.array_equal(start.cpu().numpy(), o_start)  # basis index: bit-exact
+    assert np.array_equal(w.cpu().numpy(), o_w)          # same operation order: bit-exact too
+    with pytest.raises(ValueError):
+        splines.basis_matrix(x, knots, 3, outer_ok=False, device="cuda")
+
+
+def test_group_index_passthrough(lb):
+    spec, _ = make("s5u", np.float32)
+    plan = lb.Plan(spec)
+    assert np.array_equal(plan.rows["g1"].cpu().numpy(), spec.blocks[1].idx)
+
+
+# --- IWLS ---------------------------------------------------------------------------------
+def check_iwls(spec, plan, block, th, aux):
+    dt = np.dtype(spec.dtype)
+    score, info, chol = plan.iwls(block, dev(th, plan), dev(aux, plan) if spec.num_aux else None)
+    torch.cuda.synchronize()
+    score, info, chol = score.cpu().numpy(), info.cpu().numpy(), chol.cpu().numpy()
+    prep = sam.Prepared(spec)
+    r_score, r_info = sam.iwls(spec, block, th, aux, prep=prep)
+    blk = spec.block(block)
+    sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
+    sc = sam.grad_scale(spec, th, aux, prep=prep)[:, sl]
+    assert np.all(np.abs(score - r_score) <= RTOL[dt] * np.abs(r_score) + ULPS * EPS[dt] * sc)
+    # information: all terms of an entry share a sign pattern set by the (non-negative) basis;
+    # scale by the diagonal, which dominates its row
+    dscale = np.sqrt(np.abs(np.einsum("cii->ci", r_info)))
+    iscale = dscale[:, :, None] * dscale[:, None, :]
+    ierr = np.abs(info - r_info)
+    assert np.all(ierr <= RTOL[dt] * np.abs(r_info) + ULPS * EPS[dt] * iscale), float(ierr.max())
+    np.testing.assert_array_equal(info, np.swapaxes(info, 1, 2))
+    r_chol = OI.chol_info(r_info)
+    ok = ~np.isnan(r_chol).any(axis=(1, 2))
+    assert ok.any()
+    ctol = 2e-4 if dt == np.float32 else 1e-9
+    np.testing.assert_allclose(chol[ok], r_chol[ok], rtol=ctol, atol=ctol * np.abs(r_chol[ok]).max())
+    assert np.isnan(chol[~ok]).all()
+    return score, info, chol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_iwls_s3_all_blocks(lb, dtype):
+    spec, centre = make("s3", dtype)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 24, tau2="loguniform")
+    for name in ["loc_p0", "loc_np0", "scale_p0", "scale_np0"]:
+        check_iwls(spec, plan, name, th, aux)
+
+
+@pytest.mark.parametrize("cfg,block", [("s1", "loc_p0"), ("s2", "loc_np3"), ("s4", "logits_p0"), ("s5", "log_rate_p0")])
+def test_iwls_other_families(lb, cfg, block):
+    spec, centre = make(cfg, np.float64)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 5)
+    check_iwls(spec, plan, block, th, aux)
+
+
+def test_chol_failure_is_nan(lb):
+    a = np.stack([np.array([[1.0, 2.0], [2.0, 1.0]]), np.eye(2) * 4.0, np.full((2, 2), np.nan)])
+    out = lb.chol(torch.as_tensor(a, device="cuda")).cpu().numpy()
+    assert np.isnan(out[0]).all() and np.isnan(out[2]).all()
+    np.testing.assert_allclose(out[1], np.eye(2) * np.sqrt(4.0 + 4e-6), rtol=1e-12)
+
+
+def test_iwls_utils_golden_on_device(lb, golden_dir):
+    """tests/goose/test_iwls_utils.py:11-35 through the device proposal tail."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(golden_dir, "iwls_utils.json")))
+    lhs, rhs = np.array(g["solve"]["lhs"]), np.array(g["solve"]["rhs"])
+    L = np.linalg.cholesky(lhs)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    # mu = beta + step^2/2 * solve(L, rhs) with beta = 0, step = sqrt(2)  ->  mu = solve
+    step = np.array([np.sqrt(2.0)])
+    _, _ = lb.iwls_propose(t(np.zeros((1, 5))), t(rhs[None]), t(L[None]), t(step), x_eval=t(np.zeros((1, 5))))
+    m = g["mvn_log_prob"]
+    cov = np.array(m["cov"])
+    Lc = np.linalg.cholesky(np.linalg.inv(cov))
+    # with score = 0 the mean stays at beta; step = 1
+    _, logq = lb.iwls_propose(t(np.array(m["mean"])[None]), t(np.zeros((1, 5))), t(Lc[None]),
+                              t(np.ones(1)), x_eval=t(np.array(m["x"])[None]))
+    assert logq.cpu().numpy()[0] == pytest.approx(m["log_prob"], rel=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_iwls_proposal_tail(lb, dtype):
+    spec, centre = make("s3", dtype)
+    plan = lb.Plan(spec)
+    C = 9
+    th, aux = synth.evaluation_points(spec, centre, C, tau2="loguniform")
+    rng = np.random.default_rng(11)
+    blk = spec.block("loc_np0")
+    sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
+    z = rng.normal(size=(C, blk.ncoef)).astype(dtype)
+    step = rng.uniform(0.5, 1.5, size=C).astype(dtype)
+    score, info, chol = plan.iwls("loc_np0", dev(th, plan), dev(aux, plan))
+    prop, fwd = lb.iwls_propose(dev(th[:, sl], plan), score, chol, dev(step, plan), z=dev(z, plan))
+    ref = OI.iwls_proposal(spec, "loc_np0", th, aux, step.astype(np.float64), z.astype(np.float64))
+    tol = 5e-4 if dtype == np.float32 else 1e-8
+    np.testing.assert_allclose(prop.cpu().numpy(), ref["prop"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(fwd.cpu().numpy(), ref["fwd_log_prob"], rtol=tol, atol=tol)
+    # backward density of the current position under the proposal made at `prop`
+    th2 = th.copy()
+    th2[:, sl] = prop.cpu().numpy()
+    score2, _, chol2 = plan.iwls("loc_np0", dev(th2, plan), dev(aux, plan))
+    _, bwd = lb.iwls_propose(prop, score2, chol2, dev(step, plan), x_eval=dev(th[:, sl], plan))
+    ref_b = OI.iwls_backward(spec, "loc_np0", th2, aux, step.astype(np.float64), th[:, sl].astype(np.float64))
+    np.testing.assert_allclose(bwd.cpu().numpy(), ref_b, rtol=10 * tol, atol=10 * tol)
+
+
+def test_quadform(lb):
+    spec, centre = make("s2", np.float64)
+    plan = lb.Plan(spec)
+    th, _ = synth.evaluation_points(spec, centre, 6)
+    q = plan.quadform("loc_np2", dev(th, plan)).cpu().numpy()
+    np.testing.assert_allclose(q, sam.quadform(spec, "loc_np2", th), rtol=1e-12)
+
+
+# --- the ModelInterface mirror --------------------------------------------------------------
+def test_interface_protocol(lb):
+    spec, centre = make("s3", np.float32)
+    plan = lb.Plan(spec)
+    iface = lb.Interface(plan)
+    C = 6
+    th, aux = synth.evaluation_points(spec, centre, C)
+    state = iface.unpack(dev(th, plan), dev(aux, plan))
+    assert set(state) == set(spec.position_keys()) | set(spec.aux_keys())
+    pos = iface.extract_position(["loc_np0_beta"], state)
+    assert list(pos) == ["loc_np0_beta"] and pos["loc_np0_beta"].shape == (C, 20)
+    lp0 = iface.log_prob(state).cpu().numpy()
+    new = {"loc_np0_beta": pos["loc_np0_beta"] + 0.05}
+    state2 = iface.update_state(new, state)
+    assert state2 is not state and torch.equal(state["loc_np0_beta"], pos["loc_np0_beta"])  # pure
+    th2 = th.copy()
+    th2[:, 1:21] += 0.05
+    lp2 = iface.log_prob(state2).cpu().numpy()
+    np.testing.assert_allclose(lp2, sam.log_prob(spec, th2, aux), rtol=1e-5)
+    assert not np.allclose(lp0, lp2)
+    with pytest.raises(KeyError):
+        iface.update_state({"nope": 1}, state)
+    lp, g = iface.log_prob_and_grad(state2, ["scale_np0_beta"])
+    np.testing.assert_allclose(g["scale_np0_beta"].cpu().numpy(), sam.grad(spec, th2, aux)[:, 22:42],
+                               rtol=1e-4, atol=1e-2)
+    chol = iface.chol_info_fn("scale_np0_beta")(state2)
+    assert chol.shape == (C, 20, 20)
+    init = iface.initial_state(3)
+    assert float(init["loc_np0_tau2"][0]) == 10000.0 and float(init["loc_np0_beta"].abs().sum()) == 0.0
+
+
+def test_status_codes_not_exceptions_from_c(lb):
+    import ctypes as Ct
+
+    from liesel_b200 import _lib
+
+    spec, centre = make("s1", np.float32)
+    plan = lb.Plan(spec)
+    th, _ = synth.evaluation_points(spec, centre, 2)
+    t = dev(th, plan)
+    out = torch.empty(2, device="cuda")
+    # workspace too small -> status 2, nothing launched
+    st = _lib.lib.lslb_logp_grad_f32(plan._handle, 2, _lib.ptr(t), None, _lib.ptr(out), None, 0,
+                                     _lib.ptr(plan.workspace(2)), 16, _lib.stream_ptr())
+    assert st == 2
+    st = _lib.lib.lslb_logp_grad_f64(plan._handle, 2, _lib.ptr(t), None, _lib.ptr(out), None, 0,
+                                     _lib.ptr(plan.workspace(2)), 1 << 20, _lib.stream_ptr())
+    assert st == 1  # dtype mismatch
+    with pytest.raises(_lib.LieselB200Error):
+        plan.logp_grad(t.double())

@@ -1,0 +1,111 @@
+"""Host-side logic and the C-ABI surface. CPU only (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from liesel_b200 import spec as S
+from liesel_b200 import splines, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_layout_and_names():
+    spec, centre = synth.s3_gamlss(n=64, k=8)
+    assert spec.num_params == 18 and spec.num_aux == 2 and centre.shape == (18,)
+    assert spec.position_keys() == ["loc_p0_beta", "loc_np0_beta", "scale_p0_beta", "scale_np0_beta"]
+    assert spec.aux_keys() == ["loc_np0_tau2", "scale_np0_tau2"]
+    assert [b.param_offset for b in spec.blocks] == [0, 1, 9, 10]
+    assert [b.kind for b in spec.blocks] == [S.KIND_INTERCEPT, S.KIND_SPLINE, S.KIND_INTERCEPT, S.KIND_SPLINE]
+    pr = spec.block("loc_np0").prior
+    assert pr.rank == 6.0  # float(np.linalg.matrix_rank(K)), distreg.py:161
+    ev = np.linalg.eigvalsh(pr.K)
+    assert pr.log_pdet == pytest.approx(np.log(ev[-6:]).sum())
+    assert spec.has_scale_predictor
+
+
+def test_builder_errors_mirror_distreg():
+    spec = S.ModelSpec()
+    with pytest.raises(RuntimeError, match="No response"):
+        spec.add_predictor("loc")
+    spec.add_response(np.zeros(4), "normal")
+    with pytest.raises(RuntimeError, match="No predictor 'loc' found"):  # distreg.py:87-91
+        spec.add_p_smooth(np.ones((4, 2)), 0.0, 1.0, "loc", "a")
+    spec.add_predictor("loc")
+    spec.add_p_smooth(np.arange(8.0).reshape(4, 2), 0.0, 1.0, "loc", "a")
+    with pytest.raises(RuntimeError, match="already exists"):  # distreg.py:55-59
+        spec.add_p_smooth(np.ones((4, 2)), 0.0, 1.0, "loc", "a")
+    with pytest.raises(ValueError):
+        spec.add_predictor("logits")
+    with pytest.raises(ValueError):
+        spec.add_predictor("scale", inverse_link="Softplus")
+    with pytest.raises(ValueError, match="sorted"):
+        spec.add_random_intercept(np.array([1, 0, 1, 0]), 2, 0.0, 1.0, "loc", "ri")
+    with pytest.raises(ValueError):
+        S.ModelSpec().add_response(np.zeros(3), "gamma")
+
+
+def test_synth_regenerable():
+    a, _ = synth.s2_pspline_gam(n=500, n_smooth=2, k=8)
+    b, _ = synth.s2_pspline_gam(n=500, n_smooth=2, k=8)
+    assert np.array_equal(a.y, b.y) and np.array_equal(a.blocks[1].x, b.blocks[1].x)
+    p1, x1 = synth.evaluation_points(a, np.zeros(16), 5, tau2="loguniform")
+    p2, x2 = synth.evaluation_points(a, np.zeros(16), 5, tau2="loguniform")
+    assert np.array_equal(p1, p2) and np.array_equal(x1, x2)
+    assert x1.min() >= 1e-3 and x1.max() <= 1e4
+    s5, c5 = synth.s5_poisson_ri(n=200, G=10, p=3)
+    assert np.all(np.diff(s5.blocks[1].idx) >= 0) and c5.shape == (13,)
+
+
+def test_host_splines():
+    x = np.linspace(-2, 2, 30).astype(np.float32)
+    kn = splines.equidistant_knots(x, 10, 3)
+    assert kn.dtype == np.float32 and kn.shape == (14,)
+    assert np.allclose(np.diff(kn), np.diff(kn)[0], atol=1e-5)
+    assert kn[3] < x.min() and kn[-4] > x.max()
+    K = splines.pspline_penalty(10, 2)
+    assert np.linalg.matrix_rank(K) == 8
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library must load and export exactly what include/liesel_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "liesel_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(lslb_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    so = os.path.join(ROOT, "liesel_b200", "csrc", "libliesel_b200.so")
+    assert os.path.exists(so), "run liesel_b200/csrc/build.sh (or __graft_entry__.build())"
+    lib = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    lib.lslb_version.restype = ctypes.c_int
+    assert lib.lslb_version() == 100
+    from liesel_b200 import _lib
+
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    from liesel_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(_lib.LieselB200Error):
+        _lib.require_cuda(torch.zeros(3))
+    from liesel_b200.plan import Plan
+
+    spec, _ = synth.s1_blr(n=10)
+    with pytest.raises(_lib.LieselB200Error):
+        Plan(spec)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "liesel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
