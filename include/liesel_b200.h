@@ -194,6 +194,20 @@ int lslb_spline_basis_f32(const float* x, int64_t n, const float* knots, int nkn
 int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int nknots,
                           int32_t* start, double* weights, lslb_stream_t stream);
 
+/*
+ * Measurement hooks (used by bench.py; no effect on results).
+ * lslb_debug_set_events: the given cudaEvent_t pair is recorded on the call's stream immediately
+ *   before and after the dominant row-streaming kernel of every following lslb_logp_grad_* /
+ *   lslb_iwls_* call made from this host thread (NULL, NULL switches it off).
+ * lslb_debug_pipe_peak: micro-benchmarks giving measured pipe peaks; kind 0 = FP32 FMA,
+ *   1 = packed fma.rn.f32x2, 2 = MUFU ex2, 3 = shared-memory 4-byte loads. *work (host) receives
+ *   the operations one launch performs.
+ */
+int lslb_debug_set_events(void* start_event, void* stop_event);
+int lslb_debug_event_count(void);
+int lslb_debug_pipe_peak(int kind, int blocks, int iters, float* sink, double* work,
+                         lslb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,7 +85,14 @@ for _sfx in ("f32", "f64"):
     f.restype = _i
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
 
+lib.lslb_debug_set_events.restype = _i
+lib.lslb_debug_set_events.argtypes = [_vp, _vp]
+lib.lslb_debug_event_count.restype = _i
+lib.lslb_debug_pipe_peak.restype = _i
+lib.lslb_debug_pipe_peak.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_double), _vp]
+
 EXPORTS = [
+    "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
     "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_variant",
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",

@@ -557,12 +557,14 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
     LSLB_LAUNCH_CHECK();
   }
   int st = LSLB_ERR_INVALID;
+  debug_record_start(stream);
   switch (plan->fam) {
     case FAM_NORMAL_LS: st = iwls_dispatch<T, FAM_NORMAL_LS>(plan, ep, q, k, smem, stream); break;
     case FAM_NORMAL_FIXED: st = iwls_dispatch<T, FAM_NORMAL_FIXED>(plan, ep, q, k, smem, stream); break;
     case FAM_BERNOULLI: st = iwls_dispatch<T, FAM_BERNOULLI>(plan, ep, q, k, smem, stream); break;
     case FAM_POISSON: st = iwls_dispatch<T, FAM_POISSON>(plan, ep, q, k, smem, stream); break;
   }
+  debug_record_stop(stream);
   if (st != LSLB_OK) return st;
   long long ne = (long long)(p + p * p) * k.Cpad;
   iwls_finalize_kernel<T><<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(

@@ -526,12 +526,14 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
 
   const bool g = grad != nullptr;
   int st = LSLB_ERR_INVALID;
+  debug_record_start(stream);
   switch (plan->fam) {
     case FAM_NORMAL_LS: st = dispatch_structure<T, FAM_NORMAL_LS>(plan, ep, k, g, smem, stream); break;
     case FAM_NORMAL_FIXED: st = dispatch_structure<T, FAM_NORMAL_FIXED>(plan, ep, k, g, smem, stream); break;
     case FAM_BERNOULLI: st = dispatch_structure<T, FAM_BERNOULLI>(plan, ep, k, g, smem, stream); break;
     case FAM_POISSON: st = dispatch_structure<T, FAM_POISSON>(plan, ep, k, g, smem, stream); break;
   }
+  debug_record_stop(stream);
   if (st != LSLB_OK) return st;
 
   if (g) {

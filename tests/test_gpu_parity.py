@@ -147,7 +147,7 @@ def test_nan_inf_propagate(lb):
     spec, centre = make("s5", np.float32)
     plan = lb.Plan(spec)
     th, aux = synth.evaluation_points(spec, centre, 4)
-    th[1, 0] = 200.0  # exp overflow in the Poisson rate
+    th[1, 0] = 2000.0  # exp overflow in the Poisson rate (X[:, 0] = 0.3)
     th[2, 1] = np.nan
     logp, grad = plan.logp_grad(dev(th, plan), None)
     logp = logp.cpu().numpy()
