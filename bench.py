@@ -135,10 +135,20 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+
+    def wait_started(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -167,8 +177,12 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                   "reasons": sorted(reasons), "samples": len(sm), "power_w_max": float(max(pw))}
+            # samples taken while the GPU was actually loaded: power above the midpoint of the range
+            thr = 0.5 * (min(pw) + max(pw))
+            load = [c for c, w in zip(sm, pw) if w >= thr] or sm
+            out = {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)),
+                   "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load),
+                   "power_w_max": float(max(pw))}
         return out
 
 
@@ -237,13 +251,26 @@ def run_ours(args):
     def step():
         plan.logp_grad(d_th, d_aux, want_grad=True, out=(logp, grad))
 
-    for _ in range(W):
+    # clocks are sampled from before the warm-up until the end of the e2e loop; every buffer the
+    # timed loops need is allocated first so the GPU stays loaded while the sampler runs
+    h_th = torch.as_tensor(th).pin_memory()
+    h_aux = torch.as_tensor(aux).pin_memory()
+    h_logp = torch.empty(C_, dtype=torch.float32).pin_memory()
+    h_grad = torch.empty((C_, P), dtype=torch.float32).pin_memory()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
+    t_w = time.perf_counter()
+    nwarm = 0
+    while nwarm < W or time.perf_counter() - t_w < 0.5:  # >= W steps and >= 0.5 s under load
         flush.zero_()
         step()
+        nwarm += 1
+        if nwarm % 16 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
 
     # ---- timed region: value (inputs resident in HBM) ------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for a, b in kev:  # force creation of the underlying cudaEvent_t handles
@@ -272,10 +299,6 @@ def run_ours(args):
     value = C_ * world * K / (total_ms_max * 1e-3)
 
     # ---- e2e: host buffers -> public API -> host buffers --------------------------------
-    h_th = torch.as_tensor(th).pin_memory()
-    h_aux = torch.as_tensor(aux).pin_memory()
-    h_logp = torch.empty(C_, dtype=torch.float32).pin_memory()
-    h_grad = torch.empty((C_, P), dtype=torch.float32).pin_memory()
     keys = spec.position_keys()
 
     def e2e_step():

@@ -178,7 +178,7 @@ __device__ __forceinline__ void kahan_add(T& hi, T& lo, T x) {
 }
 
 template <typename T>
-struct Vec4 {
+struct alignas(16) Vec4 {
   T a, b, c, d;
 };
 __device__ __forceinline__ Vec4<float> ld4(const float* p) {
@@ -213,6 +213,7 @@ struct lslb_plan {
   int nchunks;
   long long* d_chunk_start;  // device [nchunks+1]
   double lik_const;
+  bool rows_sorted;  // every smooth's knot span changes rarely from row to row
   int variant;
   const char* variant_name;
 };
@@ -238,6 +239,14 @@ struct LaunchCfg {
   int TC, Cpad, ntiles, fstride, nchunks;
 };
 LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain);
+struct BandedCfg {
+  int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
+};
+bool banded_fast_eligible(const lslb_plan* plan);  // banded.cu
+BandedCfg banded_cfg(const lslb_plan* plan, int C);
+template <typename T>
+int launch_banded(const lslb_plan* plan, const EvalParams<T>& ep, const BandedCfg& k, bool want_grad,
+                  cudaStream_t st);
 void fill_finalize_params(const lslb_plan* plan, FinalizeParams& fp, int C, int Cpad, int nchunks,
                           unsigned flags);
 template <typename T>

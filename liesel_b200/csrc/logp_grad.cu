@@ -330,6 +330,21 @@ static size_t eval_smem_per_chain(const lslb_plan* plan) {
   return (size_t)2 * plan->Psmall * (plan->desc.dtype == LSLB_F32 ? 4 : 8);
 }
 
+// launch geometry of the logp/grad pass: the TMA run-length kernel when the plan qualifies
+static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
+  if (banded_fast_eligible(plan)) {
+    BandedCfg b = banded_cfg(plan, C);
+    LaunchCfg k;
+    k.TC = b.TC;
+    k.Cpad = b.Cpad;
+    k.ntiles = b.ntiles_chain;
+    k.fstride = 0;
+    k.nchunks = b.nchunks;
+    return k;
+  }
+  return choose_cfg(plan, C, eval_smem_per_chain(plan));
+}
+
 template <typename T>
 struct WsLayout {
   T *pT, *partial, *bT, *gbT, *gpl;
@@ -365,7 +380,7 @@ size_t iwls_workspace_bytes(const lslb_plan* plan, int C);  // iwls.cu
 
 size_t workspace_bytes(const lslb_plan* plan, int C) {
   if (C < 1) return 0;
-  LaunchCfg k = choose_cfg(plan, C, eval_smem_per_chain(plan));
+  LaunchCfg k = eval_cfg(plan, C);
   size_t a = plan->desc.dtype == LSLB_F32 ? layout_ws<float>(plan, k, nullptr).bytes
                                           : layout_ws<double>(plan, k, nullptr).bytes;
   size_t b = iwls_workspace_bytes(plan, C);
@@ -489,8 +504,9 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (!plan || C < 1 || !params || !logp || !ws) return LSLB_ERR_INVALID;
   if (plan->A > 0 && !aux) return LSLB_ERR_INVALID;
   if ((plan->desc.dtype == LSLB_F32) != (sizeof(T) == 4)) return LSLB_ERR_INVALID;
-  LaunchCfg k = choose_cfg(plan, C, eval_smem_per_chain(plan));
-  size_t smem = eval_smem_per_chain(plan) * k.TC;
+  const bool fast = banded_fast_eligible(plan);
+  LaunchCfg k = eval_cfg(plan, C);
+  size_t smem = fast ? 0 : eval_smem_per_chain(plan) * k.TC;
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -527,6 +543,9 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   const bool g = grad != nullptr;
   int st = LSLB_ERR_INVALID;
   debug_record_start(stream);
+  if (fast) {
+    st = launch_banded<T>(plan, ep, banded_cfg(plan, C), g, stream);
+  } else
   switch (plan->fam) {
     case FAM_NORMAL_LS: st = dispatch_structure<T, FAM_NORMAL_LS>(plan, ep, k, g, smem, stream); break;
     case FAM_NORMAL_FIXED: st = dispatch_structure<T, FAM_NORMAL_FIXED>(plan, ep, k, g, smem, stream); break;

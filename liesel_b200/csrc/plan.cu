@@ -28,6 +28,20 @@ __global__ void fine_bounds_kernel(long long n, int F, const int* __restrict__ g
   fine[f] = r;
 }
 
+// number of rows whose span differs from the previous row's (one block, setup time)
+__global__ void span_changes_kernel(const int* __restrict__ start, long long n, unsigned long long* out) {
+  __shared__ unsigned long long sh[1024];
+  unsigned long long acc = 0;
+  for (long long i = 1 + threadIdx.x; i < n; i += blockDim.x) acc += start[i] != start[i - 1];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
 // sum_i lgamma(y_i + 1) in double, one block, fixed order (deterministic)
 template <typename T>
 __global__ void lgamma_sum_kernel(const T* __restrict__ y, long long n, double* out) {
@@ -174,6 +188,21 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
       cudaFree(d_out);
     }
   }
+  // are the rows ordered for long constant-span runs?
+  p->rows_sorted = p->ns > 0;
+  if (p->ns > 0 && e == cudaSuccess) {
+    unsigned long long* d_cnt = nullptr;
+    e = cudaMalloc(&d_cnt, sizeof(unsigned long long) * LSLB_MAX_SPL);
+    if (e == cudaSuccess) {
+      unsigned long long h[LSLB_MAX_SPL] = {0};
+      for (int m = 0; m < p->ns; ++m)
+        span_changes_kernel<<<1, 1024>>>(p->blk[p->sp[m]].index, n, d_cnt + m);
+      e = cudaMemcpy(h, d_cnt, sizeof(unsigned long long) * p->ns, cudaMemcpyDeviceToHost);
+      for (int m = 0; m < p->ns; ++m)
+        if ((long long)h[m] > n / 64 + 64) p->rows_sorted = false;
+      cudaFree(d_cnt);
+    }
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -186,7 +215,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   // kernel variant
   if (p->grp < 0 && p->nd == 0 && p->ns >= 1) {
     p->variant = VAR_BANDED;
-    p->variant_name = "banded_runlength";
+    p->variant_name = banded_fast_eligible(p) ? "banded_tma_runlength" : "banded_runlength";
   } else if (p->ns == 0 && p->nd == 1 && p->blk[p->dn[0]].ncoef <= 16) {
     p->variant = VAR_DENSE_REG;
     p->variant_name = "dense_registers";

@@ -47,6 +47,7 @@ def make(cfg, dtype):
         "s2": lambda: synth.s2_pspline_gam(n=20_000, dtype=dtype),
         "s3": lambda: synth.s3_gamlss(n=50_000, dtype=dtype),
         "s4": lambda: synth.s4_logistic(n=4000, p=48, dtype=dtype),
+        "s4s": lambda: synth.s4_logistic(n=4000, p=12, dtype=dtype),
         "s5": lambda: synth.s5_poisson_ri(n=20_000, G=500, dtype=dtype),
         "s5u": lambda: synth.s5_poisson_ri(n=20_000, G=700, dtype=dtype, balanced=False),
     }[cfg]()
@@ -217,7 +218,7 @@ def test_iwls_s3_all_blocks(lb, dtype):
         check_iwls(spec, plan, name, th, aux)
 
 
-@pytest.mark.parametrize("cfg,block", [("s1", "loc_p0"), ("s2", "loc_np3"), ("s4", "logits_p0"), ("s5", "log_rate_p0")])
+@pytest.mark.parametrize("cfg,block", [("s1", "loc_p0"), ("s2", "loc_np3"), ("s4s", "logits_p0"), ("s5", "log_rate_p0")])
 def test_iwls_other_families(lb, cfg, block):
     spec, centre = make(cfg, np.float64)
     plan = lb.Plan(spec)
