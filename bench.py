@@ -192,7 +192,7 @@ def measure_pipe_peaks(torch, _lib, sm_count):
 
     sink = torch.zeros(4, device="cuda")
     res = {}
-    for kind, name, iters in [(0, "ffma", 4000), (1, "ffma2", 4000), (2, "mufu_ex2", 2000), (3, "lds32", 4000)]:
+    for kind, name, iters in [(0, "ffma", 4000), (1, "ffma2", 4000), (7, "ffma_3reg", 4000), (2, "mufu_ex2", 2000)]:
         work = C.c_double(0.0)
         best = None
         for rep in range(4):
@@ -210,7 +210,7 @@ def measure_pipe_peaks(torch, _lib, sm_count):
         "fp32_fma_tflops": 2 * res["ffma"] / 1e12,
         "fp32_ffma2_tflops": 2 * res["ffma2"] / 1e12,
         "mufu_ex2_tops": res["mufu_ex2"] / 1e12,
-        "lds_tbps": 4 * res["lds32"] / 1e12,
+        "fp32_fma_3_distinct_registers_tflops": 2 * res["ffma_3reg"] / 1e12,
     }
 
 

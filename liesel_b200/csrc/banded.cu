@@ -11,6 +11,8 @@
 //     row data are shared-memory broadcasts; when the span changes (rare) the accumulators are
 //     flushed into this CTA's private slice of the partial buffer (coalesced global RMW);
 //   * no atomics: fixed-order reduction over chunks happens in finalize (logp_grad.cu).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lslb {
@@ -301,14 +303,19 @@ bool banded_fast_eligible(const lslb_plan* plan) {
   return true;
 }
 
+// float32 with more than 128 chains: two chains per thread, packed f32x2 math (banded_x2.cu)
+static bool use_x2(const lslb_plan* plan, int C) { return plan->desc.dtype == LSLB_F32 && C > 128; }
+
 BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   BandedCfg k;
-  k.TC = 128;
+  const bool x2 = use_x2(plan, C);
+  k.TC = x2 ? 256 : 128;  // chains per CTA
   k.Cpad = (C + k.TC - 1) / k.TC * k.TC;
   k.ntiles_chain = k.Cpad / k.TC;
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
-  const int ctas_per_sm = 6;
+  int ctas_per_sm = x2 ? 5 : 6;
+  if (const char* e = getenv("LSLB_BANDED_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;  // tuning knob
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles_chain - 1) / k.ntiles_chain;
   if (want < 1) want = 1;
   if (want > k.ntiles_total) want = k.ntiles_total;
@@ -326,9 +333,15 @@ static int banded_launch(const EvalParams<T>& ep, const BandedCfg& k, bool g, cu
   return LSLB_OK;
 }
 
+int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const BandedCfg& k, bool g,
+                     cudaStream_t st);  // banded_x2.cu
+
 template <typename T>
 int launch_banded(const lslb_plan* plan, const EvalParams<T>& ep, const BandedCfg& k, bool g,
                   cudaStream_t st) {
+  if constexpr (sizeof(T) == 4) {
+    if (k.TC == 256) return launch_banded_x2(plan, ep, k, g, st);
+  }
   if (plan->fam == FAM_NORMAL_LS) {
     if (plan->ns == 1) return banded_launch<T, FAM_NORMAL_LS, 1>(ep, k, g, st);
     return banded_launch<T, FAM_NORMAL_LS, 2>(ep, k, g, st);

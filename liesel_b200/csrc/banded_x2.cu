@@ -1,0 +1,358 @@
+// Headline kernel (H / S3, float32): the run-length banded evaluation of banded.cu with TWO chains
+// per thread, computed with Blackwell's packed FP32 instructions (fma/mul/add .f32x2 -> FFMA2 etc.).
+//
+// Why packed: a packed instruction does two chains' worth of FP32 work per issue slot, which frees
+// issue bandwidth for the shared-memory broadcasts and MUFU ops that accompany the 16 FMAs of a row.
+//
+// Data flow per CTA (128 threads = 256 chains, one row chunk):
+//   TMA bulk copies (the caller's SoA arrays, 128-row tiles, 3-stage ring, mbarrier complete_tx)
+//   -> all warps run the row loop on the tile with shared-memory broadcasts. A row's weights are
+//   scalars shared by both chains of a thread: FFMA2 takes them as a 32-bit operand broadcast to
+//   both halves (SASS `Rn.F32`), so nothing is duplicated in shared memory and the register file
+//   reads one register instead of a pair.
+//
+// Register-file bandwidth, not the FMA pipe, is the first limit of this loop: an FFMA2 with three
+// distinct register-PAIR operands needs 3 RF cycles, one with a broadcast scalar or a reused
+// operand 2 (tools/microbench.py: 3-register scalar FFMA reaches 45 of 72 TFLOP/s). Rows are
+// therefore processed four at a time, ordered so that the coefficient operand (forward) and the
+// residual operand (backward) repeat in consecutive instructions and the operand-reuse cache
+// serves them.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace lslb {
+
+constexpr int XR = 128;     // rows per tile
+constexpr int XSTAGES = 3;  // ring depth
+typedef unsigned long long u64;
+
+__device__ __forceinline__ unsigned x_smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ u64 bc(float v) {  // {v, v}: ptxas folds this into a .F32 broadcast operand
+  u64 r;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int NS>
+struct XRaw {  // what the TMA engine writes: the caller's SoA arrays, one tile
+  float w[NS][XR * 4];
+  float y[XR];
+  int start[NS][XR];
+};
+
+// PM: bit m set <=> smooth m feeds predictor 1 (log scale)
+template <int FAM, int NS, int PM, bool GRAD>
+__global__ void __launch_bounds__(128, 5)
+banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
+  __shared__ __align__(128) XRaw<NS> raw[XSTAGES];
+  __shared__ __align__(8) u64 full[XSTAGES];
+
+  const int tid = threadIdx.x;
+  const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
+  const int ch = blockIdx.y;
+  const int tile0 = ch * tiles_per_cta;
+  const int my_tiles = min(tile0 + tiles_per_cta, ntiles_total) - tile0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < XSTAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_rows = [&](int t) -> int {
+    long long rem = p.n - (long long)t * XR;
+    return rem >= XR ? XR : (int)rem;
+  };
+  auto bulk = [&](void* dst, const void* src, unsigned bytes, u64* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            x_smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(x_smem_u32(bar))
+        : "memory");
+  };
+  auto issue = [&](int t, int s) {
+    const long long r0 = (long long)t * XR;
+    constexpr unsigned bytes = XR * 4 + NS * (XR * 16 + XR * 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(&full[s])),
+                 "r"(bytes)
+                 : "memory");
+    bulk(raw[s].y, p.y + r0, XR * 4, &full[s]);
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      bulk(raw[s].w[m], p.sp[m].w + 4 * r0, XR * 16, &full[s]);
+      bulk(raw[s].start[m], p.sp[m].start + r0, XR * 4, &full[s]);
+    }
+  };
+  auto wait_full = [&](int s, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
+          : "=r"(ok)
+          : "r"(x_smem_u32(&full[s])), "r"(parity)
+          : "memory");
+    }
+  };
+
+  if (tid == 0) {
+    for (int k = 0; k < XSTAGES - 1 && k < my_tiles; ++k)
+      if (tile_rows(tile0 + k) == XR) issue(tile0 + k, k);
+  }
+
+  // ---- per-thread state: two chains ------------------------------------------------------------
+  const size_t ldc = (size_t)p.Cpad;
+  auto ld2 = [&](int j) -> u64 { return *reinterpret_cast<const u64*>(p.pT + (size_t)j * ldc + c); };
+  float* mine = p.partial + (size_t)ch * (p.Psmall + LSLB_NACC) * ldc + c;
+  auto at2 = [&](int j) -> u64* { return reinterpret_cast<u64*>(mine + (size_t)j * ldc); };
+
+  u64 o0 = pk(0.f, 0.f), o1 = pk(0.f, 0.f);
+  for (int q = 0; q < p.ni; ++q) {
+    const u64 v = ld2(p.ic[q].soff);
+    if (p.ic[q].pred) o1 = add2(o1, v); else o0 = add2(o0, v);
+  }
+  if constexpr (GRAD) {
+    for (int j = 0; j < p.Psmall; ++j) *at2(j) = pk(0.f, 0.f);
+  }
+  int cur[NS];
+  u64 wb[NS][4], wg[NS][4];
+#pragma unroll
+  for (int m = 0; m < NS; ++m) {
+    cur[m] = -1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { wb[m][t] = pk(0.f, 0.f); wg[m][t] = pk(0.f, 0.f); }
+  }
+  const u64 NEG1 = pk(-1.f, -1.f);
+  const u64 NLOG2E = pk(-1.4426950408889634f, -1.4426950408889634f);
+  const u64 INVS_FIXED = pk(p.fixed_inv_scale, p.fixed_inv_scale);
+  float lpa_hi = 0.f, lpa_lo = 0.f, lpb_hi = 0.f, lpb_lo = 0.f;  // Kahan pairs, chains a and b
+  u64 sr0 = pk(0.f, 0.f), sr1 = pk(0.f, 0.f);
+
+  auto change = [&](int m, int s) {
+    const int so = p.sp[m].soff;
+    if constexpr (GRAD) {
+      if (cur[m] >= 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          u64* q = at2(so + cur[m] + t);
+          *q = add2(*q, wg[m][t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      wb[m][t] = ld2(so + s + t);
+      wg[m][t] = pk(0.f, 0.f);
+    }
+    cur[m] = s;
+  };
+
+  for (int k = 0; k < my_tiles; ++k) {
+    const int t = tile0 + k;
+    const int s = k % XSTAGES;
+    const int rows = tile_rows(t);
+    {  // refill the stage consumed in the previous iteration (every thread passed its barrier)
+      const int kn = k + XSTAGES - 1;
+      if (tid == 0 && kn < my_tiles && tile_rows(tile0 + kn) == XR) issue(tile0 + kn, kn % XSTAGES);
+    }
+    XRaw<NS>& D = raw[s];
+    if (rows == XR) {
+      wait_full(s, (k / XSTAGES) & 1);
+    } else {  // ragged last tile: ordinary loads (bulk copies need 16-byte multiples)
+      const long long r0 = (long long)t * XR;
+      for (int r = tid; r < rows; r += blockDim.x) {
+        D.y[r] = p.y[r0 + r];
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+          D.start[m][r] = p.sp[m].start[r0 + r];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) D.w[m][4 * r + u] = p.sp[m].w[4 * (r0 + r) + u];
+        }
+      }
+      __syncthreads();
+    }
+
+    // is every smooth's span constant over this tile? (each warp evaluates it redundantly)
+    bool uni = true;
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      const int first = D.start[m][0];
+      bool eq = true;
+      for (int r = (tid & 31); r < rows; r += 32) eq = eq && (D.start[m][r] == first);
+      uni = uni && __all_sync(0xffffffffu, eq);
+    }
+
+    u64 sz2 = pk(0.f, 0.f), se1 = pk(0.f, 0.f);  // per-tile sums: z^2 and eta1
+
+    // NR consecutive rows starting at r: forward with wb fixed across rows (u-major), likelihood,
+    // backward with the residual fixed across the four weights of a row
+    auto rows_block = [&](int r, auto NRtag) {
+      constexpr int NR = decltype(NRtag)::value;
+      float w[NS][NR][4];
+      u64 eta0[NR], eta1[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) { eta0[i] = o0; eta1[i] = o1; }
+#pragma unroll
+      for (int m = 0; m < NS; ++m) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(&D.w[m][4 * (r + i)]);
+          w[m][i][0] = v.x; w[m][i][1] = v.y; w[m][i][2] = v.z; w[m][i][3] = v.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            if ((PM >> m) & 1) eta1[i] = fma2(bc(w[m][i][u]), wb[m][u], eta1[i]);
+            else eta0[i] = fma2(bc(w[m][i][u]), wb[m][u], eta0[i]);
+          }
+        }
+      }
+      u64 d0[NR], d1[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const u64 d = fma2(eta0[i], NEG1, bc(D.y[r + i]));  // y - eta0
+        u64 inv_s;
+        if constexpr (FAM == FAM_NORMAL_LS) {
+          const u64 tt = mul2(eta1[i], NLOG2E);
+          float ta, tb;
+          upk(tt, ta, tb);
+          inv_s = pk(ex2f(ta), ex2f(tb));  // exp(-eta1)
+          se1 = add2(se1, eta1[i]);
+        } else {
+          inv_s = INVS_FIXED;
+        }
+        const u64 z = mul2(d, inv_s);
+        sz2 = fma2(z, z, sz2);
+        if constexpr (GRAD) {
+          d0[i] = mul2(z, inv_s);
+          sr0 = add2(sr0, d0[i]);
+          d1[i] = d0[i];
+          if constexpr (PM != 0) d1[i] = fma2(z, z, NEG1);
+        }
+      }
+      if constexpr (GRAD) {
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            const u64 rr = ((PM >> m) & 1) ? d1[i] : d0[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wg[m][u] = fma2(bc(w[m][i][u]), rr, wg[m][u]);
+          }
+        }
+      }
+    };
+    using N1 = std::integral_constant<int, 1>;
+    using N4 = std::integral_constant<int, 4>;
+
+    if (uni) {
+#pragma unroll
+      for (int m = 0; m < NS; ++m) {
+        const int first = D.start[m][0];
+        if (first != cur[m]) change(m, first);
+      }
+      int r = 0;
+      for (; r + 4 <= rows; r += 4) rows_block(r, N4{});
+      for (; r < rows; ++r) rows_block(r, N1{});
+    } else {
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+          const int sm = D.start[m][r];
+          if (sm != cur[m]) change(m, sm);
+        }
+        rows_block(r, N1{});
+      }
+    }
+    // tile sums -> log-likelihood (row constants are added in finalize) and d/d eta1 sums
+    float z2a, z2b, e1a, e1b;
+    upk(sz2, z2a, z2b);
+    upk(se1, e1a, e1b);
+    kahan_add(lpa_hi, lpa_lo, fmaf(-0.5f, z2a, -e1a));
+    kahan_add(lpb_hi, lpb_lo, fmaf(-0.5f, z2b, -e1b));
+    if constexpr (GRAD && FAM == FAM_NORMAL_LS) {
+      const float nr = -(float)rows;
+      sr1 = add2(sr1, add2(sz2, pk(nr, nr)));  // sum (z^2 - 1)
+    }
+    __syncthreads();  // everyone is done with stage s: it may be refilled
+  }
+
+  if constexpr (GRAD) {
+#pragma unroll
+    for (int m = 0; m < NS; ++m) {
+      if (cur[m] >= 0) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          u64* q = at2(p.sp[m].soff + cur[m] + t);
+          *q = add2(*q, wg[m][t]);
+        }
+      }
+    }
+    for (int q = 0; q < p.ni; ++q) *at2(p.ic[q].soff) = p.ic[q].pred ? sr1 : sr0;
+  }
+  *at2(p.Psmall) = pk(lpa_hi, lpb_hi);
+  *at2(p.Psmall + 1) = pk(lpa_lo, lpb_lo);
+}
+
+// host ------------------------------------------------------------------------------------------
+template <int FAM, int NS, int PM>
+static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st) {
+  dim3 grid(k.ntiles_chain, k.nchunks), block(128);
+  if (g) banded_x2_kernel<FAM, NS, PM, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+  else banded_x2_kernel<FAM, NS, PM, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
+int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const BandedCfg& k, bool g,
+                     cudaStream_t st) {
+  int pm = 0;
+  for (int m = 0; m < plan->ns; ++m) pm |= (plan->blk[plan->sp[m]].predictor & 1) << m;
+  if (plan->fam == FAM_NORMAL_LS) {
+    if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st)
+                                 : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st);
+    switch (pm) {
+      case 0: return x2_launch<FAM_NORMAL_LS, 2, 0>(ep, k, g, st);
+      case 1: return x2_launch<FAM_NORMAL_LS, 2, 1>(ep, k, g, st);
+      case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st);
+      default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st);
+    }
+  }
+  if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st);
+  return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st);
+}
+
+}  // namespace lslb

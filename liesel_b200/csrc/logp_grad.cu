@@ -221,20 +221,29 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 // =======================================================================================
 // finalize
 // =======================================================================================
+// Both finalize kernels use blocks of (32 chains) x (FIN_G helpers): helper g sums the chunk
+// partials ch = g, g + FIN_G, ... in double; the FIN_G partial sums are then combined in a fixed
+// order through shared memory, so the result does not depend on scheduling.
+constexpr int FIN_G = 8;
+
 template <typename T>
-__global__ void finalize_grad_kernel(const __grid_constant__ FinalizeParams fp,
-                                     const T* __restrict__ partial, const T* __restrict__ pT,
-                                     const T* __restrict__ aux, T* __restrict__ grad) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)fp.Psmall * fp.Cpad;
-  if (idx >= total) return;
-  int c = (int)(idx % fp.Cpad);
-  int j = (int)(idx / fp.Cpad);
-  if (c >= fp.C) return;
+__global__ void __launch_bounds__(32 * FIN_G)
+finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
+                     const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad) {
+  __shared__ double red[FIN_G][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y;
+  const int g = threadIdx.y;
   double acc = 0.0;
   const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
   const T* src = partial + (size_t)j * fp.Cpad + c;
-  for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+  for (int ch = g; ch < fp.nchunks; ch += FIN_G) acc += (double)src[ch * stride];
+  red[g][threadIdx.x] = acc;
+  __syncthreads();
+  if (g != 0 || c >= fp.C) return;
+  acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
   for (int b = 0; b < fp.nblocks; ++b) {
     const PriorP& pr = fp.pr[b];
     if (pr.soff < 0 || j < pr.soff || j >= pr.soff + pr.ncoef) continue;
@@ -257,48 +266,69 @@ __global__ void finalize_grad_kernel(const __grid_constant__ FinalizeParams fp,
 }
 
 template <typename T>
-__global__ void finalize_logp_kernel(const __grid_constant__ FinalizeParams fp,
-                                     const T* __restrict__ partial, const T* __restrict__ pT,
-                                     const T* __restrict__ aux, const T* __restrict__ gpl,
-                                     int gtiles, int G, T* __restrict__ logp) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= fp.C) return;
-  const double half_log_2pi = 0.91893853320467274178;
+__global__ void __launch_bounds__(32 * FIN_G)
+finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
+                     const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
+                     int gtiles, int G, T* __restrict__ logp) {
+  __shared__ double red[FIN_G][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;  // < Cpad (Cpad is a multiple of 32)
+  const int g = threadIdx.y;
+  const bool with_prior = !(fp.flags & LSLB_SKIP_PRIOR);
   const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
   const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
   const T* lo = hi + fp.Cpad;
   double acc = 0.0;
-  for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)hi[ch * stride] - (double)lo[ch * stride];
-  acc += fp.lik_const;
-  if (!(fp.flags & LSLB_SKIP_PRIOR)) {
-    acc += fp.const_term;
+  for (int ch = g; ch < fp.nchunks; ch += FIN_G) acc += (double)hi[ch * stride] - (double)lo[ch * stride];
+  // quadratic forms of the priors, coefficient rows j = g, g + FIN_G, ... (already scaled)
+  if (with_prior) {
+    const int cc = c < fp.C ? c : 0;
     for (int b = 0; b < fp.nblocks; ++b) {
       const PriorP& pr = fp.pr[b];
       if (pr.prior == LSLB_PRIOR_NORMAL) {
         double q = 0.0;
         if (pr.soff >= 0) {
-          for (int j = 0; j < pr.ncoef; ++j) {
+          for (int j = g; j < pr.ncoef; j += FIN_G) {
             double d = (double)pT[(size_t)(pr.soff + j) * fp.Cpad + c] - pr.m;
             q += d * d;
           }
           q *= -0.5 * pr.inv_s2;
         } else {  // group block: quadratic part was reduced per 32-group tile
-          for (int t = 0; t < gtiles; ++t) q += (double)gpl[(size_t)t * fp.Cpad + c];
+          for (int t = g; t < gtiles; t += FIN_G) q += (double)gpl[(size_t)t * fp.Cpad + c];
         }
-        acc += q - (double)pr.ncoef * (pr.log_s + half_log_2pi);
+        acc += q;
       } else if (pr.prior == LSLB_PRIOR_MVND) {
         const T* K = reinterpret_cast<const T*>(pr.K);
         double q = 0.0;  // (x @ prec) @ x^T, mvn_degen.py:442
-        for (int j = 0; j < pr.ncoef; ++j) {
+        for (int j = g; j < pr.ncoef; j += FIN_G) {
           double xk = 0.0;
           for (int i = 0; i < pr.ncoef; ++i)
             xk += (double)pT[(size_t)(pr.soff + i) * fp.Cpad + c] * (double)K[(size_t)i * pr.ncoef + j];
           q += xk * (double)pT[(size_t)(pr.soff + j) * fp.Cpad + c];
         }
+        double tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)cc * fp.A + pr.tau2_slot] : pr.tau2_fixed;
+        acc += -0.5 * q / tau2;
+      }
+    }
+  }
+  red[g][threadIdx.x] = acc;
+  __syncthreads();
+  if (g != 0 || c >= fp.C) return;
+  const double half_log_2pi = 0.91893853320467274178;
+  acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
+  acc += fp.lik_const;
+  if (with_prior) {
+    acc += fp.const_term;
+    for (int b = 0; b < fp.nblocks; ++b) {
+      const PriorP& pr = fp.pr[b];
+      if (pr.prior == LSLB_PRIOR_NORMAL) {
+        acc -= (double)pr.ncoef * (pr.log_s + half_log_2pi);
+      } else if (pr.prior == LSLB_PRIOR_MVND) {
         double tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)c * fp.A + pr.tau2_slot] : pr.tau2_fixed;
         double log_tau2 = log(tau2);
-        // 0.5 * (-x'Kx/tau2 - (rank*log(2 pi) - (log_pdet - rank*log tau2)))
-        acc += 0.5 * (-q / tau2 - (pr.rank * 2.0 * half_log_2pi - (pr.log_pdet - pr.rank * log_tau2)));
+        // 0.5 * (-x'Kx/tau2 - (rank*log(2 pi) - (log_pdet - rank*log tau2))): constants here
+        acc += -0.5 * (pr.rank * 2.0 * half_log_2pi - (pr.log_pdet - pr.rank * log_tau2));
         if (pr.has_ig && pr.tau2_slot >= 0)
           acc += pr.ig_const - (pr.ig_a + 1.0) * log_tau2 - pr.ig_b / tau2;
       }
@@ -558,8 +588,8 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (g) {
     long long total = (long long)plan->Psmall * k.Cpad;
     if (total > 0) {
-      finalize_grad_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fp, L.partial,
-                                                                                   L.pT, aux, grad);
+      dim3 fgrid(k.Cpad / 32, plan->Psmall), fblock(32, FIN_G);
+      finalize_grad_kernel<T><<<fgrid, fblock, 0, stream>>>(fp, L.partial, L.pT, aux, grad);
       LSLB_LAUNCH_CHECK();
     }
     if (plan->grp >= 0) {
@@ -569,8 +599,8 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
       LSLB_LAUNCH_CHECK();
     }
   }
-  finalize_logp_kernel<T><<<(C + 127) / 128, 128, 0, stream>>>(fp, L.partial, L.pT, aux, L.gpl,
-                                                               L.gtiles, G, logp);
+  finalize_logp_kernel<T><<<k.Cpad / 32, dim3(32, FIN_G), 0, stream>>>(fp, L.partial, L.pT, aux,
+                                                                       L.gpl, L.gtiles, G, logp);
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }

@@ -316,7 +316,7 @@ def test_interface_protocol(lb):
     chol = iface.chol_info_fn("scale_np0_beta")(state2)
     assert chol.shape == (C, 20, 20)
     init = iface.initial_state(3)
-    assert float(init["loc_np0_tau2"][0]) == 10000.0 and float(init["loc_np0_beta"].abs().sum()) == 0.0
+    assert float(init["loc_np0_tau2"][0]) == spec.block("loc_np0").prior.tau2_init and float(init["loc_np0_beta"].abs().sum()) == 0.0
 
 
 def test_status_codes_not_exceptions_from_c(lb):
