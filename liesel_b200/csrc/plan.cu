@@ -221,7 +221,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
     p->variant_name = "dense_registers";
   } else {
     p->variant = VAR_GENERIC;
-    p->variant_name = "generic_smem";
+    p->variant_name = dense_x2_eligible(p) ? "dense_x2_register_sliced" : "generic_smem";
   }
   *out = p;
   return LSLB_OK;

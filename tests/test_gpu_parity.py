@@ -338,3 +338,68 @@ def test_status_codes_not_exceptions_from_c(lb):
     assert st == 1  # dtype mismatch
     with pytest.raises(_lib.LieselB200Error):
         plan.logp_grad(t.double())
+
+
+# --- row sharding (S4 style), emulated on one GPU --------------------------------------------
+def test_row_sharded_partials_sum_to_full(lb):
+    """Two 'ranks' hold half the rows each; rank 1 passes LSLB_SKIP_PRIOR; partials add up."""
+    from liesel_b200 import dist as ld
+    from liesel_b200.spec import ModelSpec
+
+    spec, centre = make("s4", np.float32)
+    th, aux = synth.evaluation_points(spec, centre, 10)
+    full = lb.Plan(spec)
+    lp_full, g_full = full.logp_grad(dev(th, full))
+    acc_lp, acc_g = None, None
+    for rank in range(2):
+        a, b = ld.row_shard(spec.n, rank, 2)
+        part = ModelSpec(dtype=spec.dtype)
+        part.add_response(spec.y[a:b], "bernoulli").add_predictor("logits")
+        blk = spec.blocks[0]
+        part.add_p_smooth(blk.X[a:b], blk.prior.m, blk.prior.s, "logits", blk.name)
+        plan = lb.Plan(part)
+        lp, g = plan.logp_grad(dev(th, plan), flags=0 if rank == 0 else ld.SKIP_PRIOR)
+        acc_lp = lp if acc_lp is None else acc_lp + lp
+        acc_g = g if acc_g is None else acc_g + g
+    np.testing.assert_allclose(acc_lp.cpu().numpy(), lp_full.cpu().numpy(), rtol=2e-6)
+    scale = sam.grad_scale(spec, th)
+    assert np.all(np.abs(acc_g.cpu().numpy() - g_full.cpu().numpy()) <= 32 * 2.0**-24 * scale + 1e-6)
+    check_logp_grad(spec, full, th, aux)
+
+
+# --- register-sliced dense kernel (S4 path) ----------------------------------------------------
+@pytest.mark.parametrize("p,n,C", [(256, 3000, 70), (100, 2500, 9), (36, 777, 64), (20, 1000, 5)])
+def test_dense_x2_logistic(lb, p, n, C):
+    spec, centre = synth.s4_logistic(n=n, p=p, dtype=np.float32)
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_x2_register_sliced"
+    th, aux = synth.evaluation_points(spec, centre, C)
+    check_logp_grad(spec, plan, th, aux)
+
+
+def test_dense_x2_other_families(lb):
+    from liesel_b200.spec import ModelSpec
+
+    rng = np.random.default_rng(9)
+    n, p = 1500, 40
+    X = np.column_stack([rng.normal(size=(n, p)) * 0.2])
+    beta = rng.normal(size=p) * 0.3
+    # Poisson, dense + intercept
+    y = rng.poisson(np.exp(0.5 + X @ beta)).astype(np.float64)
+    spec = ModelSpec(dtype=np.dtype(np.float32))
+    spec.add_response(y, "poisson").add_predictor("log_rate")
+    spec.add_p_smooth(np.ones((n, 1)), 0.0, 10.0, "log_rate", "b0")
+    spec.add_p_smooth(X, 0.0, 10.0, "log_rate", "bx")
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_x2_register_sliced"
+    th, aux = synth.evaluation_points(spec, np.concatenate([[0.5], beta]), 12)
+    check_logp_grad(spec, plan, th, aux)
+    # Normal with fixed scale
+    y = X @ beta + rng.normal(size=n)
+    spec = ModelSpec(dtype=np.dtype(np.float32))
+    spec.add_response(y, "normal").add_predictor("loc")
+    spec.fixed_scale = 0.7
+    spec.add_p_smooth(X, 0.0, 10.0, "loc", "bx")
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, beta, 3)
+    check_logp_grad(spec, plan, th, aux)
