@@ -20,56 +20,9 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "x2_common.cuh"
 
 namespace lslb {
-
-constexpr int XR = 128;     // rows per tile
-constexpr int XSTAGES = 3;  // ring depth
-typedef unsigned long long u64;
-
-__device__ __forceinline__ unsigned x_smem_u32(const void* p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ u64 bc(float v) {  // {v, v}: ptxas folds this into a .F32 broadcast operand
-  u64 r;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
-  return r;
-}
-__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float ex2f(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-template <int NS>
-struct XRaw {  // what the TMA engine writes: the caller's SoA arrays, one tile
-  float w[NS][XR * 4];
-  float y[XR];
-  int start[NS][XR];
-};
 
 // PM: bit m set <=> smooth m feeds predictor 1 (log scale)
 template <int FAM, int NS, int PM, bool GRAD>

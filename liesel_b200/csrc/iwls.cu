@@ -477,6 +477,30 @@ static IwlsWs<T> iwls_layout(const lslb_plan* plan, const LaunchCfg& k, int nq, 
   return L;
 }
 
+int launch_banded_iwls_x2(const lslb_plan* plan, const EvalParams<float>& ep, int tk, int tm, int tp,
+                          int p, int nq, float* partial, const BandedCfg& k, cudaStream_t st);  // banded_iwls_x2.cu
+BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C);
+
+// packed TMA run-length IWLS kernel: float32 banded Gaussian plans, spline or intercept target
+static bool iwls_fast(const lslb_plan* plan, int tkind) {
+  return plan->desc.dtype == LSLB_F32 && banded_fast_eligible(plan) &&
+         (tkind == TK_SPLINE || tkind == TK_INTERCEPT);
+}
+
+static LaunchCfg iwls_cfg(const lslb_plan* plan, int C, int tkind, int nq) {
+  if (iwls_fast(plan, tkind)) {
+    BandedCfg b = banded_iwls_cfg(plan, C);
+    LaunchCfg k;
+    k.TC = b.TC;
+    k.Cpad = b.Cpad;
+    k.ntiles = b.ntiles_chain;
+    k.fstride = 0;
+    k.nchunks = b.nchunks;
+    return k;
+  }
+  return choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+}
+
 size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
   size_t best = 0;
   for (int b = 0; b < plan->desc.nblocks; ++b) {
@@ -485,7 +509,7 @@ size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
     int p = plan->blk[b].ncoef;
     if (p > LSLB_MAX_IWLS_P) continue;
     int nq = iwls_nq(tkind, p);
-    LaunchCfg k = choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+    LaunchCfg k = iwls_cfg(plan, C, tkind, nq);
     size_t bytes = plan->desc.dtype == LSLB_F32 ? iwls_layout<float>(plan, k, nq, nullptr).bytes
                                                 : iwls_layout<double>(plan, k, nq, nullptr).bytes;
     if (bytes > best) best = bytes;
@@ -523,8 +547,9 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
   const int p = plan->blk[block].ncoef;
   if (p > LSLB_MAX_IWLS_P) return LSLB_ERR_UNSUPPORTED;
   const int nq = iwls_nq(tkind, p);
-  LaunchCfg k = choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
-  size_t smem = iwls_smem_per_chain(plan, nq) * k.TC;
+  const bool fast = iwls_fast(plan, tkind);
+  LaunchCfg k = iwls_cfg(plan, C, tkind, nq);
+  size_t smem = fast ? 0 : iwls_smem_per_chain(plan, nq) * k.TC;
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   IwlsWs<T> L = iwls_layout<T>(plan, k, nq, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -558,6 +583,11 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
   }
   int st = LSLB_ERR_INVALID;
   debug_record_start(stream);
+  if (fast) {
+    if constexpr (sizeof(T) == 4)
+      st = launch_banded_iwls_x2(plan, ep, tkind == TK_SPLINE ? 0 : 1, tidx, q.tpred, p, nq,
+                                 reinterpret_cast<float*>(L.partial), banded_iwls_cfg(plan, C), stream);
+  } else
   switch (plan->fam) {
     case FAM_NORMAL_LS: st = iwls_dispatch<T, FAM_NORMAL_LS>(plan, ep, q, k, smem, stream); break;
     case FAM_NORMAL_FIXED: st = iwls_dispatch<T, FAM_NORMAL_FIXED>(plan, ep, q, k, smem, stream); break;
