@@ -119,8 +119,8 @@ class Plan:
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h is not None and h.value:
-            _lib.lib.lslb_plan_destroy(h)
+        if h is not None and h.value and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.lslb_plan_destroy(h)  # (module globals may already be gone at interpreter exit)
             h.value = None
 
     # -- workspace ------------------------------------------------------------------
