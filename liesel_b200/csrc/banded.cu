@@ -314,7 +314,7 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.ntiles_chain = k.Cpad / k.TC;
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
-  int ctas_per_sm = x2 ? 5 : 6;
+  int ctas_per_sm = x2 ? 4 : 6;
   if (const char* e = getenv("LSLB_BANDED_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;  // tuning knob
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles_chain - 1) / k.ntiles_chain;
   if (want < 1) want = 1;

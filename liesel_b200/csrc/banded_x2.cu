@@ -26,7 +26,7 @@ namespace lslb {
 
 // PM: bit m set <=> smooth m feeds predictor 1 (log scale)
 template <int FAM, int NS, int PM, bool GRAD>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
   __shared__ __align__(128) XRaw<NS> raw[XSTAGES];
   __shared__ __align__(8) u64 full[XSTAGES];
@@ -169,21 +169,15 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
     u64 sz2 = pk(0.f, 0.f), se1 = pk(0.f, 0.f);  // per-tile sums: z^2 and eta1
 
-    // NR consecutive rows starting at r: forward with wb fixed across rows (u-major), likelihood,
-    // backward with the residual fixed across the four weights of a row
-    auto rows_block = [&](int r, auto NRtag) {
+    // NR rows whose weights/responses are already in registers: forward with wb fixed across rows
+    // (u-major), likelihood, backward with the residual fixed across the four weights of a row
+    auto compute_block = [&](const float (&w)[NS][4][4], const float (&yv)[4], auto NRtag) {
       constexpr int NR = decltype(NRtag)::value;
-      float w[NS][NR][4];
       u64 eta0[NR], eta1[NR];
 #pragma unroll
       for (int i = 0; i < NR; ++i) { eta0[i] = o0; eta1[i] = o1; }
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          const float4 v = *reinterpret_cast<const float4*>(&D.w[m][4 * (r + i)]);
-          w[m][i][0] = v.x; w[m][i][1] = v.y; w[m][i][2] = v.z; w[m][i][3] = v.w;
-        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -196,7 +190,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       u64 d0[NR], d1[NR];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
-        const u64 d = fma2(eta0[i], NEG1, bc(D.y[r + i]));  // y - eta0
+        const u64 d = fma2(eta0[i], NEG1, bc(yv[i]));  // y - eta0
         u64 inv_s;
         if constexpr (FAM == FAM_NORMAL_LS) {
           const u64 tt = mul2(eta1[i], NLOG2E);
@@ -228,6 +222,22 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
         }
       }
     };
+    auto load_block = [&](float (&w)[NS][4][4], float (&yv)[4], int r, auto NRtag) {
+      constexpr int NR = decltype(NRtag)::value;
+#pragma unroll
+      for (int m = 0; m < NS; ++m)
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(&D.w[m][4 * (r + i)]);
+          w[m][i][0] = v.x; w[m][i][1] = v.y; w[m][i][2] = v.z; w[m][i][3] = v.w;
+        }
+      if constexpr (NR == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(&D.y[r]);
+        yv[0] = v.x; yv[1] = v.y; yv[2] = v.z; yv[3] = v.w;
+      } else {
+        yv[0] = D.y[r];
+      }
+    };
     using N1 = std::integral_constant<int, 1>;
     using N4 = std::integral_constant<int, 4>;
 
@@ -237,17 +247,36 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
         const int first = D.start[m][0];
         if (first != cur[m]) change(m, first);
       }
-      int r = 0;
-      for (; r + 4 <= rows; r += 4) rows_block(r, N4{});
-      for (; r < rows; ++r) rows_block(r, N1{});
+      if (rows == XR) {
+        // software pipeline over 4-row blocks: the next block's weights are loaded into a second
+        // register set while the current block computes, so all operands of a block are ready
+        // together and the forward FMAs can be issued coefficient-major (operand reuse)
+        float wa[NS][4][4], wbuf[NS][4][4], ya[4], yb[4];
+        load_block(wa, ya, 0, N4{});
+#pragma unroll 1
+        for (int r = 0; r < XR; r += 8) {
+          load_block(wbuf, yb, r + 4, N4{});
+          compute_block(wa, ya, N4{});
+          if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
+          compute_block(wbuf, yb, N4{});
+        }
+      } else {
+        float w1[NS][4][4], y1[4];
+        for (int r = 0; r < rows; ++r) {
+          load_block(w1, y1, r, N1{});
+          compute_block(w1, y1, N1{});
+        }
+      }
     } else {
+      float w1[NS][4][4], y1[4];
       for (int r = 0; r < rows; ++r) {
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
           const int sm = D.start[m][r];
           if (sm != cur[m]) change(m, sm);
         }
-        rows_block(r, N1{});
+        load_block(w1, y1, r, N1{});
+        compute_block(w1, y1, N1{});
       }
     }
     // tile sums -> log-likelihood (row constants are added in finalize) and d/d eta1 sums

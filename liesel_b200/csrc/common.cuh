@@ -242,6 +242,10 @@ LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain);
 struct BandedCfg {
   int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
 };
+bool dgroup_x2_eligible(const lslb_plan* plan);  // dgroup_x2.cu
+LaunchCfg dgroup_x2_cfg(const lslb_plan* plan, int C);
+int launch_dgroup_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k,
+                     bool want_grad, cudaStream_t st);
 bool dense_x2_eligible(const lslb_plan* plan);  // dense_x2.cu
 BandedCfg dense_x2_cfg(const lslb_plan* plan, int C);
 int launch_dense_x2(const lslb_plan* plan, const EvalParams<float>& ep, const BandedCfg& k,

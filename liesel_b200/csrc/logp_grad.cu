@@ -363,6 +363,7 @@ static size_t eval_smem_per_chain(const lslb_plan* plan) {
 // launch geometry of the logp/grad pass: the TMA run-length kernel when the plan qualifies
 static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
   const bool dense = dense_x2_eligible(plan);
+  if (!dense && dgroup_x2_eligible(plan)) return dgroup_x2_cfg(plan, C);
   if (dense || banded_fast_eligible(plan)) {
     BandedCfg b = dense ? dense_x2_cfg(plan, C) : banded_cfg(plan, C);
     LaunchCfg k;
@@ -536,9 +537,10 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (plan->A > 0 && !aux) return LSLB_ERR_INVALID;
   if ((plan->desc.dtype == LSLB_F32) != (sizeof(T) == 4)) return LSLB_ERR_INVALID;
   const bool dense = dense_x2_eligible(plan);
-  const bool fast = !dense && banded_fast_eligible(plan);
+  const bool dgrp = !dense && dgroup_x2_eligible(plan);
+  const bool fast = !dense && !dgrp && banded_fast_eligible(plan);
   LaunchCfg k = eval_cfg(plan, C);
-  size_t smem = (fast || dense) ? 0 : eval_smem_per_chain(plan) * k.TC;
+  size_t smem = (fast || dense || dgrp) ? 0 : eval_smem_per_chain(plan) * k.TC;
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -577,6 +579,8 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   debug_record_start(stream);
   if (dense) {
     if constexpr (sizeof(T) == 4) st = launch_dense_x2(plan, ep, dense_x2_cfg(plan, C), g, stream);
+  } else if (dgrp) {
+    if constexpr (sizeof(T) == 4) st = launch_dgroup_x2(plan, ep, k, g, stream);
   } else if (fast) {
     st = launch_banded<T>(plan, ep, banded_cfg(plan, C), g, stream);
   } else

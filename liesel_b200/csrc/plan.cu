@@ -218,7 +218,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
     p->variant_name = banded_fast_eligible(p) ? "banded_tma_runlength" : "banded_runlength";
   } else if (p->ns == 0 && p->nd == 1 && p->blk[p->dn[0]].ncoef <= 16) {
     p->variant = VAR_DENSE_REG;
-    p->variant_name = "dense_registers";
+    p->variant_name = dgroup_x2_eligible(p) ? "dense_group_x2_tma" : "dense_registers";
   } else {
     p->variant = VAR_GENERIC;
     p->variant_name = dense_x2_eligible(p) ? "dense_x2_register_sliced" : "generic_smem";
