@@ -195,6 +195,21 @@ int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int n
                           int32_t* start, double* weights, lslb_stream_t stream);
 
 /*
+ * Fused per-leaf bookkeeping of the batched NUTS driver (liesel_b200/nuts.py; the trajectory code
+ * the reference delegates to BlackJAX, src/liesel/goose/nuts.py:254-260). `ptrs` is a HOST array of
+ * 23 device pointers: q_e, r_e, g_e, q_n, r_half, g_n, lp_n, eps, inv_mass, h0, q_s, g_s, lp_s,
+ * logw_s, rsum_s, ck_r, ck_s, sum_acc, n_leaf, act, turn_s, div_s, u; `ints` = {C, P, D1, odd, lo, hi}.
+ *   pre : r_half = r_e + eps/2 * g_e;  q_n = q_e + eps * inv_mass * r_half
+ *   post: r_n, energy error, divergence, multinomial proposal update, momentum sum, checkpointed
+ *         U-turn test (odd leaves: checkpoints lo..hi; even leaves store checkpoint hi), edge update,
+ *         activity mask. Chains with act == 0 are left untouched.
+ */
+int lslb_nuts_leaf_pre_f32(void* const* ptrs, const int* ints, lslb_stream_t stream);
+int lslb_nuts_leaf_pre_f64(void* const* ptrs, const int* ints, lslb_stream_t stream);
+int lslb_nuts_leaf_post_f32(void* const* ptrs, const int* ints, double div_thr, lslb_stream_t stream);
+int lslb_nuts_leaf_post_f64(void* const* ptrs, const int* ints, double div_thr, lslb_stream_t stream);
+
+/*
  * Measurement hooks (used by bench.py; no effect on results).
  * lslb_debug_set_events: the given cudaEvent_t pair is recorded on the call's stream immediately
  *   before and after the dominant row-streaming kernel of every following lslb_logp_grad_* /

@@ -85,6 +85,14 @@ for _sfx in ("f32", "f64"):
     f.restype = _i
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
 
+for _sfx in ("f32", "f64"):
+    f = getattr(lib, "lslb_nuts_leaf_pre_" + _sfx)
+    f.restype = _i
+    f.argtypes = [C.POINTER(_vp), C.POINTER(_i), _vp]
+    f = getattr(lib, "lslb_nuts_leaf_post_" + _sfx)
+    f.restype = _i
+    f.argtypes = [C.POINTER(_vp), C.POINTER(_i), C.c_double, _vp]
+
 lib.lslb_debug_set_events.restype = _i
 lib.lslb_debug_set_events.argtypes = [_vp, _vp]
 lib.lslb_debug_event_count.restype = _i
@@ -93,6 +101,7 @@ lib.lslb_debug_pipe_peak.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_double), _vp
 
 EXPORTS = [
     "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
+    "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
     "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_variant",
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",

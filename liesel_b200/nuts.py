@@ -79,8 +79,16 @@ class BatchedNUTS:
     def __init__(self, logp_grad_fn: Callable, q0: torch.Tensor, max_treedepth: int = 10,
                  da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
                  da_t0: int = 10, divergence_threshold: float = 1000.0, seed: int = 0,
-                 initial_step_size: float | None = None):
+                 initial_step_size: float | None = None, fused: bool | None = None,
+                 logp_grad_into: Callable | None = None):
+        """
+        ``fused`` (default: on for CUDA tensors): run the per-leaf bookkeeping in the two CUDA kernels
+        ``lslb_nuts_leaf_pre/post`` instead of ~30 torch ops. ``logp_grad_into(q, logp_out, grad_out)``
+        optionally evaluates into preallocated buffers (``Plan.logp_grad(..., out=...)``).
+        """
         self.f = logp_grad_fn
+        self.f_into = logp_grad_into
+        self.fused = bool(q0.is_cuda) if fused is None else bool(fused)
         self.q = q0.clone()
         self.C, self.P = q0.shape
         self.dev, self.dt = q0.device, q0.dtype
@@ -165,6 +173,57 @@ class BatchedNUTS:
     def _da_finalize(self):
         self.step_size = torch.exp(self.da_log_avg)
 
+    # -- fused subtree (CUDA kernels for the per-leaf bookkeeping) ----------------------------------
+    def _subtree_fused(self, j, q_e, r_e, g_e, eps, h0, alive, lp_prop, U, ck_r, ck_s):
+        import ctypes as Ct
+
+        from . import _lib
+
+        C, P, dev, dt = self.C, self.P, self.dev, self.dt
+        st = self._fused_state if hasattr(self, "_fused_state") else None
+        if st is None:
+            z2 = lambda: torch.empty((C, P), dtype=dt, device=dev)
+            z1 = lambda: torch.empty(C, dtype=dt, device=dev)
+            st = {k: z2() for k in ("q_e", "r_e", "g_e", "q_n", "r_half", "g_n", "q_s", "g_s", "rsum_s")}
+            st.update({k: z1() for k in ("lp_n", "lp_s", "logw_s", "sum_acc", "n_leaf", "eps", "h0")})
+            st.update({k: torch.empty(C, dtype=torch.uint8, device=dev) for k in ("act", "turn_s", "div_s")})
+            self._fused_state = st
+        st["q_e"].copy_(q_e); st["r_e"].copy_(r_e); st["g_e"].copy_(g_e)
+        st["q_s"].copy_(q_e); st["g_s"].copy_(g_e); st["lp_s"].copy_(lp_prop)
+        st["logw_s"].fill_(-float("inf")); st["rsum_s"].zero_()
+        st["sum_acc"].zero_(); st["n_leaf"].zero_()
+        st["eps"].copy_(eps); st["h0"].copy_(h0)
+        st["act"].copy_(alive.to(torch.uint8)); st["turn_s"].zero_(); st["div_s"].zero_()
+        inv_mass = self.inv_mass.contiguous()
+        sfx = _lib.sfx(dt)
+        pre = getattr(_lib.lib, "lslb_nuts_leaf_pre_" + sfx)
+        post = getattr(_lib.lib, "lslb_nuts_leaf_post_" + sfx)
+        order = ["q_e", "r_e", "g_e", "q_n", "r_half", "g_n", "lp_n"]
+        tens = [st[k] for k in order] + [st["eps"], inv_mass, st["h0"], st["q_s"], st["g_s"], st["lp_s"],
+                                         st["logw_s"], st["rsum_s"], ck_r, ck_s, st["sum_acc"], st["n_leaf"],
+                                         st["act"], st["turn_s"], st["div_s"], U]
+        ptrs = (Ct.c_void_p * 23)(*[t.data_ptr() for t in tens])
+        ints = (Ct.c_int * 6)(C, P, ck_r.shape[1], 0, 0, 0)
+        stream = _lib.stream_ptr()
+        n_leaves = 2 ** j
+        for i in range(n_leaves):
+            if i in (1, 3, 7, 15, 31, 63, 127, 255, 511) and not bool(st["act"].any()):
+                break  # (checked at a few points only: every check is a host sync)
+            lo, hi = _leaf_idx_to_ckpt_idxs(i)
+            ints[3], ints[4], ints[5] = i & 1, lo, hi
+            ptrs[22] = U[i].data_ptr()
+            _lib.check(pre(ptrs, ints, stream), "lslb_nuts_leaf_pre")
+            if self.f_into is not None:
+                self.f_into(st["q_n"], st["lp_n"], st["g_n"])
+            else:
+                lp, g = self.f(st["q_n"])
+                st["lp_n"].copy_(lp); st["g_n"].copy_(g)
+            self.evals += 1
+            _lib.check(post(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+        return (st["q_e"].clone(), st["r_e"].clone(), st["g_e"].clone(), st["q_s"].clone(), st["lp_s"].clone(),
+                st["g_s"].clone(), st["logw_s"].clone(), st["rsum_s"].clone(), st["turn_s"].bool(),
+                st["div_s"].bool(), st["sum_acc"].clone(), st["n_leaf"].clone())
+
     # -- one NUTS transition for all chains ---------------------------------------------------
     @torch.no_grad()
     def transition(self) -> NUTSInfo:
@@ -202,7 +261,13 @@ class BatchedNUTS:
             turn_s = torch.zeros(C, dtype=torch.bool, device=dev)
             div_s = torch.zeros(C, dtype=torch.bool, device=dev)
             act = alive.clone()
-            for i in range(2 ** j):
+            U = self._rand(2 ** j, C)
+            if self.fused:
+                q_e, r_e, g_e, q_s, lp_s, g_s, logw_s, rsum_s, turn_s, div_s, sa, nl = self._subtree_fused(
+                    j, q_e, r_e, g_e, eps, h0, alive, lp_prop, U, ck_r, ck_s)
+                sum_acc = sum_acc + sa
+                n_leaf = n_leaf + nl
+            for i in range(0 if self.fused else 2 ** j):
                 if not bool(act.any()):
                     break
                 q_n, r_n, lp_n, g_n = self._leapfrog(q_e, r_e, g_e, eps)
@@ -214,7 +279,7 @@ class BatchedNUTS:
                 m = act[:, None]
                 # multinomial (progressive uniform) sampling inside the subtree
                 logw_new = torch.logaddexp(logw_s, logw_n)
-                take = act & (torch.log(self._rand(C)) < logw_n - logw_new)
+                take = act & (torch.log(U[i]) < logw_n - logw_new)
                 tk = take[:, None]
                 q_s = torch.where(tk, q_n, q_s)
                 g_s = torch.where(tk, g_n, g_s)

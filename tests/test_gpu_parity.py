@@ -403,3 +403,29 @@ def test_dense_x2_other_families(lb):
     plan = lb.Plan(spec)
     th, aux = synth.evaluation_points(spec, beta, 3)
     check_logp_grad(spec, plan, th, aux)
+
+
+# --- fused NUTS leaf kernels vs the torch reference path ----------------------------------------
+def test_nuts_fused_matches_torch_path(lb):
+    from liesel_b200.nuts import BatchedNUTS
+
+    spec, centre = synth.s3_gamlss(n=3000, k=8, dtype=np.float64)
+    plan = lb.Plan(spec)
+    C = 24
+    th, aux = synth.evaluation_points(spec, centre, C)
+    q0, a = dev(th, plan), dev(aux, plan)
+    f = lambda q: plan.logp_grad(q.contiguous(), a)
+    into = lambda q, lp, g: plan.logp_grad(q, a, out=(lp, g))
+    s_ref = BatchedNUTS(f, q0, seed=5, fused=False, initial_step_size=0.02, max_treedepth=6)
+    s_fus = BatchedNUTS(f, q0, seed=5, fused=True, initial_step_size=0.02, max_treedepth=6,
+                        logp_grad_into=into)
+    for _ in range(4):
+        i_ref, i_fus = s_ref.transition(), s_fus.transition()
+        assert torch.equal(i_ref.treedepth, i_fus.treedepth)
+        assert torch.equal(i_ref.error_code, i_fus.error_code)
+        assert torch.equal(i_ref.leapfrog, i_fus.leapfrog)
+        np.testing.assert_allclose(i_fus.acceptance_prob.cpu().numpy(), i_ref.acceptance_prob.cpu().numpy(),
+                                   rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(s_fus.q.cpu().numpy(), s_ref.q.cpu().numpy(), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(s_fus.logp.cpu().numpy(), s_ref.logp.cpu().numpy(), rtol=1e-10)
+    assert int(i_ref.treedepth.max()) >= 3  # trajectories long enough to exercise the checkpoints

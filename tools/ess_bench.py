@@ -34,6 +34,7 @@ th0, aux0 = synth.evaluation_points(spec, centre, C, seed=args.seed)
 gen = torch.Generator().manual_seed(args.seed)
 gib = [(b, b.prior) for b in spec.blocks if b.tau2_slot >= 0]
 
+f_into = None
 if args.cpu:
     from oracle.cpu_port import CpuPort
 
@@ -59,7 +60,10 @@ else:
     aux = torch.as_tensor(aux0, device=dev)
 
     def f(q):
-        return plan.logp_grad(q, aux)
+        return plan.logp_grad(q.contiguous(), aux)
+
+    def f_into(q, lp, g):
+        plan.logp_grad(q, aux, out=(lp, g))
 
     def quad(blk, q):
         return plan.quadform(blk.name, q.contiguous()).double()
@@ -78,7 +82,7 @@ def gibbs(s):
 
 q0 = torch.as_tensor(th0, device=dev)
 t0 = time.perf_counter()
-s = BatchedNUTS(f, q0, seed=args.seed)
+s = BatchedNUTS(f, q0, seed=args.seed, logp_grad_into=f_into)
 winfo = s.warmup(args.warmup, hook=gibbs)
 sync()
 t1 = time.perf_counter()
