@@ -1,0 +1,148 @@
+"""
+Batched IWLS-within-Gibbs sampler for distributional regression models: the device-side
+counterpart of what ``dist_reg_mcmc`` configures in the reference (``model/distreg.py:300-349``):
+an ``IWLSKernel`` per coefficient block (``distreg.py:113-121,194-201``) and a Gibbs kernel per
+smoothing variance (``tau2_gibbs_kernel``, ``distreg.py:277-297``).
+
+One IWLS transition follows ``IWLSKernel._standard_transition`` (``goose/iwls.py:299-345``):
+
+    score, chol(info)        at the current position                         (:320-321)
+    mu = beta + step^2/2 * solve(chol, score);  prop ~ N(mu, (chol/step)^-T (chol/step)^-1)  (:323-324)
+    forward log q                                                             (:327)
+    score, chol(info)        at the proposal;  backward log q                (:331-336)
+    Metropolis-Hastings step with correction = bwd - fwd  (``goose/mh.py:17-71``)
+    error codes: 2 = indefinite information, identity fallback (``_safe_chol``, :245-290); 90 = NaN
+    acceptance probability (``mh.py:53-57``); step size by dual averaging during warm-up
+    (defaults ``initial_step_size=0.01``, ``da_target_accept=0.8``, :134-145).
+
+Score, information and Cholesky come from ONE pass over the rows per evaluation point
+(``Plan.iwls``), the proposal algebra from ``lslb_iwls_propose``; the log-posterior of the current
+state is carried along (the reference reads it from the cached model state, ``mh.py:48``).
+All chains advance in lock-step; every tensor has a leading chain axis.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .plan import Plan, iwls_propose
+
+
+class IWLSGibbsSampler:
+    def __init__(self, plan: Plan, params: torch.Tensor, aux: torch.Tensor | None, seed: int = 0,
+                 blocks: list[str] | None = None, initial_step_size: float = 0.01,
+                 da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
+                 da_t0: int = 10, gibbs: bool = True):
+        self.plan, self.spec = plan, plan.spec
+        self.params = params.clone().contiguous()
+        self.aux = None if aux is None else aux.clone().contiguous()
+        self.C = params.shape[0]
+        self.dev, self.dt = params.device, params.dtype
+        self.blocks = [b for b in self.spec.blocks if b.kind != 2 and (blocks is None or b.name in blocks)]
+        self.gibbs_blocks = [b for b in self.spec.blocks if gibbs and b.tau2_slot >= 0 and b.prior.ig_a is not None]
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(seed)
+        self.target, self.gamma, self.kappa, self.t0 = da_target_accept, da_gamma, da_kappa, da_t0
+        self.step = {b.name: torch.full((self.C,), initial_step_size, dtype=self.dt, device=self.dev)
+                     for b in self.blocks}
+        self._da_init()
+        self.logp, _ = plan.logp_grad(self.params, self.aux, want_grad=False)
+        self.logp = self.logp.clone()
+        self.evals = {"iwls": 0, "logp": 1}
+
+    # -- dual averaging (goose/da.py) ----------------------------------------------------------
+    def _da_init(self):
+        self.da = {k: {"err": torch.zeros_like(v), "avg": torch.log(v), "mu": torch.log(10.0 * v)}
+                   for k, v in self.step.items()}
+
+    def _da_step(self, name, acc, t_in_epoch):
+        t = t_in_epoch + 1
+        d = self.da[name]
+        d["err"] = d["err"] + (self.target - acc)
+        log_step = d["mu"] - d["err"] * math.sqrt(t) / (self.gamma * (self.t0 + t))
+        self.step[name] = torch.exp(log_step)
+        eta = t ** (-self.kappa)
+        d["avg"] = (1 - eta) * d["avg"] + eta * log_step
+
+    def _da_finalize(self):
+        for k in self.step:
+            self.step[k] = torch.exp(self.da[k]["avg"])
+
+    # -- pieces ----------------------------------------------------------------------------------
+    def _safe_chol(self, chol):
+        """``_safe_chol`` with ``fallback_chol_info="identity"`` (iwls.py:245-290): code 2."""
+        bad = torch.isnan(chol).flatten(1).any(dim=1)
+        eye = torch.eye(chol.shape[-1], dtype=chol.dtype, device=chol.device)
+        chol = torch.where(bad[:, None, None], eye, chol)
+        return chol.contiguous(), bad.to(torch.int32) * 2
+
+    def iwls_transition(self, blk, adapt_t: int | None = None):
+        sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
+        step = self.step[blk.name]
+        pos = self.params[:, sl].contiguous()
+        score, _, chol = self.plan.iwls(blk.name, self.params, self.aux)
+        chol, code = self._safe_chol(chol)
+        z = torch.randn(pos.shape, generator=self.gen, device=self.dev, dtype=self.dt)
+        prop, fwd = iwls_propose(pos, score, chol, step, z=z)
+        params_prop = self.params.clone()
+        params_prop[:, sl] = prop
+        score_p, _, chol_p = self.plan.iwls(blk.name, params_prop, self.aux)
+        chol_p, _ = self._safe_chol(chol_p)
+        _, bwd = iwls_propose(prop, score_p, chol_p, step, x_eval=pos)
+        lp_prop, _ = self.plan.logp_grad(params_prop, self.aux, want_grad=False)
+        self.evals["iwls"] += 2
+        self.evals["logp"] += 1
+        log_acc = lp_prop - self.logp + (bwd - fwd)
+        nan = torch.isnan(log_acc)
+        log_acc = torch.where(nan, torch.full_like(log_acc, -float("inf")), log_acc)  # mh.py:53-57
+        code = code + nan.to(torch.int32) * 90
+        acc = torch.exp(torch.clamp(log_acc, max=0.0))
+        u = torch.rand(self.C, generator=self.gen, device=self.dev, dtype=self.dt)
+        accept = u <= acc
+        self.params = torch.where(accept[:, None], params_prop, self.params).contiguous()
+        self.logp = torch.where(accept, lp_prop, self.logp)
+        if adapt_t is not None:
+            self._da_step(blk.name, acc, adapt_t)
+        return {"error_code": code, "acceptance_prob": acc, "position_moved": accept}
+
+    def gibbs_transition(self, blk):
+        """tau2 | beta ~ InverseGamma(a + rank/2, b + beta'K beta/2) (distreg.py:277-297)."""
+        pr = blk.prior
+        a = pr.ig_a + 0.5 * pr.rank
+        b = pr.ig_b + 0.5 * self.plan.quadform(blk.name, self.params).double()
+        gam = torch._standard_gamma(torch.full((self.C,), a, dtype=torch.float64, device=self.dev),
+                                    generator=self.gen)
+        self.aux[:, blk.tau2_slot] = (b / gam).to(self.dt)
+
+    def sweep(self, adapt_t: int | None = None):
+        infos = {}
+        for blk in self.blocks:
+            infos[blk.name] = self.iwls_transition(blk, adapt_t)
+        if self.gibbs_blocks:
+            for blk in self.gibbs_blocks:
+                self.gibbs_transition(blk)
+            self.logp, _ = self.plan.logp_grad(self.params, self.aux, want_grad=False)
+            self.logp = self.logp.clone()
+            self.evals["logp"] += 1
+        return infos
+
+    def warmup(self, num: int):
+        self._da_init()
+        out = [self.sweep(adapt_t=t) for t in range(num)]
+        self._da_finalize()
+        return out
+
+    def sample(self, num: int):
+        P = self.params.shape[1]
+        A = 0 if self.aux is None else self.aux.shape[1]
+        draws = torch.empty((num, self.C, P), dtype=self.dt, device=self.dev)
+        aux_draws = torch.empty((num, self.C, A), dtype=self.dt, device=self.dev)
+        infos = []
+        for t in range(num):
+            infos.append(self.sweep())
+            draws[t] = self.params
+            if A:
+                aux_draws[t] = self.aux
+        return draws, aux_draws, infos

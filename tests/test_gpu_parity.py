@@ -429,3 +429,35 @@ def test_nuts_fused_matches_torch_path(lb):
         np.testing.assert_allclose(s_fus.q.cpu().numpy(), s_ref.q.cpu().numpy(), rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(s_fus.logp.cpu().numpy(), s_ref.logp.cpu().numpy(), rtol=1e-10)
     assert int(i_ref.treedepth.max()) >= 3  # trajectories long enough to exercise the checkpoints
+
+
+# --- IWLS-within-Gibbs sampler: the reference's own kernel integration pins ------------------------
+def test_iwls_sampler_recovers_model_lm(lb, golden_dir):
+    """tests/goose/kernels/test_iwls.py via model_lm.py:70-84: posterior means within 5 % of OLS,
+    mean acceptance within 0.05 of the dual-averaging target."""
+    import json
+    import os
+
+    from liesel_b200.iwls_sampler import IWLSGibbsSampler
+    from liesel_b200.spec import ModelSpec
+
+    g = json.load(open(os.path.join(golden_dir, "model_lm.json")))
+    X, y = np.array(g["X"]), np.array(g["y"])
+    spec = ModelSpec(dtype=np.dtype(np.float64))
+    spec.add_response(y, "normal").add_predictor("loc").add_predictor("scale")
+    spec.add_p_smooth(X, 0.0, None, "loc", "beta")
+    spec.add_p_smooth(np.ones((30, 1)), 0.0, None, "scale", "log_sigma")
+    plan = lb.Plan(spec)
+    C = 8
+    q0 = torch.tensor([g["beta"] + [g["log_sigma"]]], dtype=torch.float64, device="cuda").repeat(C, 1)
+    s = IWLSGibbsSampler(plan, q0, None, seed=42)
+    s.warmup(1500)
+    draws, _, infos = s.sample(1500)
+    d = draws.cpu().numpy()
+    assert d[:, :, :2].mean(axis=(0, 1)) == pytest.approx(np.array(g["beta_ols"]), rel=0.05)
+    assert d[:, :, 2].mean() == pytest.approx(np.log(g["sigma_ols"]), rel=0.05)
+    for name in ["beta", "log_sigma"]:
+        acc = np.mean([float(i[name]["acceptance_prob"].mean()) for i in infos])
+        assert acc == pytest.approx(0.8, abs=0.05), (name, acc)
+        codes = torch.cat([i[name]["error_code"] for i in infos])
+        assert float((codes == 0).float().mean()) > 0.99
