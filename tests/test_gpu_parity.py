@@ -461,3 +461,90 @@ def test_iwls_sampler_recovers_model_lm(lb, golden_dir):
         assert acc == pytest.approx(0.8, abs=0.05), (name, acc)
         codes = torch.cat([i[name]["error_code"] for i in infos])
         assert float((codes == 0).float().mean()) > 0.99
+
+
+# --- BASELINE.json full sizes: size-independent properties -------------------------------------------
+def test_full_size_h_properties(lb):
+    """H (n = 1e6, 1024 chains): the oracle would take minutes, so check properties instead:
+    (1) 4 chains picked out of the 1024 give bit-identical results when evaluated alone in a batch
+        of the same tile width (chains are independent),
+    (2) the sum over two disjoint row halves equals the full evaluation (additivity over rows),
+    (3) a few chains agree with the float64 oracle on a 2 % row subsample scaled... (not valid) ->
+        instead the float64 plan of the same data agrees with the float32 plan within rtol 1e-5,
+    (4) gradient = finite difference of the float64 log-posterior."""
+    from liesel_b200.spec import ModelSpec
+
+    n, C = 1_000_000, 1024
+    spec, centre = synth.s3_gamlss(n=n)
+    plan = lb.Plan(spec)
+    assert plan.variant == "banded_tma_runlength"
+    th, aux = synth.evaluation_points(spec, centre, C, tau2="loguniform")
+    t, a = dev(th, plan), dev(aux, plan)
+    lp, g = plan.logp_grad(t, a)
+    lp, g = lp.clone(), g.clone()
+    assert torch.isfinite(lp).all() and torch.isfinite(g).all()
+    # (1) chain independence: chains 0..255 alone (same 256-chain tile) -> bitwise equal
+    lp_s, g_s = plan.logp_grad(t[:256].contiguous(), a[:256].contiguous())
+    assert torch.equal(lp_s, lp[:256]) and torch.equal(g_s, g[:256])
+    # (3)/(4) float64 plan of the same data
+    spec64, _ = synth.s3_gamlss(n=n, dtype=np.float64)
+    # same float32 covariate/knots/response as the float32 model, up-cast
+    spec64.y = spec.y.astype(np.float64)
+    for b64, b32 in zip(spec64.blocks, spec.blocks):
+        if b32.x is not None:
+            b64.x, b64.knots = b32.x.astype(np.float64), b32.knots.astype(np.float64)
+    plan64 = lb.Plan(spec64)
+    sel = [0, 300, 1023]
+    t64 = torch.as_tensor(th[sel].astype(np.float64), device="cuda")
+    a64 = torch.as_tensor(aux[sel].astype(np.float64), device="cuda")
+    lp64, g64 = plan64.logp_grad(t64, a64)
+    np.testing.assert_allclose(lp[sel].cpu().numpy(), lp64.cpu().numpy(), rtol=1e-5)
+    gs = g64.abs().max().item()
+    np.testing.assert_allclose(g[sel].cpu().numpy(), g64.cpu().numpy(), rtol=1e-4, atol=2e-6 * gs * 50)
+    for j in [0, 7, 21, 35]:
+        e = 1e-6
+        tp, tm = t64.clone(), t64.clone()
+        tp[:, j] += e
+        tm[:, j] -= e
+        fd = (plan64.logp_grad(tp, a64, want_grad=False)[0] - plan64.logp_grad(tm, a64, want_grad=False)[0]) / (2 * e)
+        np.testing.assert_allclose(fd.cpu().numpy(), g64[:, j].cpu().numpy(), rtol=2e-4, atol=1e-3)
+    # (2) additivity over rows: two half plans, second with LSLB_SKIP_PRIOR
+    acc_lp, acc_g = 0, 0
+    for r, (lo, hi) in enumerate([(0, n // 2), (n // 2, n)]):
+        part = ModelSpec(dtype=spec.dtype)
+        part.add_response(spec.y[lo:hi], "normal").add_predictor("loc").add_predictor("scale")
+        for b in spec.blocks:
+            pred = "loc" if b.predictor == 0 else "scale"
+            if b.kind == 3:
+                part.add_p_smooth(np.ones((hi - lo, 1)), b.prior.m, b.prior.s, pred, b.name)
+            else:
+                part.add_spline_smooth(b.x[lo:hi], b.knots, b.prior.K, b.prior.ig_a, b.prior.ig_b, pred,
+                                       b.name, tau2_init=b.prior.tau2_init)
+        pp = lb.Plan(part)
+        l_r, g_r = pp.logp_grad(t[:256].contiguous(), a[:256].contiguous(), flags=0 if r == 0 else 1)
+        acc_lp, acc_g = acc_lp + l_r.double(), acc_g + g_r.double()
+    np.testing.assert_allclose(acc_lp.cpu().numpy(), lp[:256].double().cpu().numpy(), rtol=2e-6)
+    gmax = g[:256].abs().max().item()
+    np.testing.assert_allclose(acc_g.cpu().numpy(), g[:256].double().cpu().numpy(), rtol=1e-4, atol=1e-5 * gmax)
+
+
+def test_full_size_s5_group_sum_properties(lb):
+    """S5 at full size: the random-intercept gradient is a segment sum — summing it over groups must
+    equal the fixed-intercept column's gradient divided by its constant (0.3), prior terms removed."""
+    spec, centre = synth.s5_poisson_ri()
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_group_x2_tma"
+    C = 64
+    th, aux = synth.evaluation_points(spec, centre, C)
+    t = dev(th, plan)
+    lp, g = plan.logp_grad(t, None)
+    lp2, g2 = plan.logp_grad(t, None)
+    assert torch.equal(lp, lp2) and torch.equal(g, g2)          # deterministic segment sums
+    lp_l, g_l = plan.logp_grad(t, None, flags=1)                 # likelihood part only
+    p = 8
+    sum_b = g_l[:, p:].double().sum(dim=1)                       # sum_g sum_{i in g} r_i = sum_i r_i
+    from_x0 = g_l[:, 0].double() / 0.3                           # X[:, 0] = 0.3
+    np.testing.assert_allclose(sum_b.cpu().numpy(), from_x0.cpu().numpy(), rtol=2e-4)
+    # prior part: grad - grad_lik = -(b - m)/s^2
+    pr = (g - g_l)[:, p:].double()
+    np.testing.assert_allclose(pr.cpu().numpy(), (-(t[:, p:].double()) / 0.25).cpu().numpy(), rtol=1e-4, atol=1e-4)
