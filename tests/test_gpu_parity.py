@@ -483,9 +483,12 @@ def test_full_size_h_properties(lb):
     lp, g = plan.logp_grad(t, a)
     lp, g = lp.clone(), g.clone()
     assert torch.isfinite(lp).all() and torch.isfinite(g).all()
-    # (1) chain independence: chains 0..255 alone (same 256-chain tile) -> bitwise equal
+    # (1) chain independence: chains 0..255 evaluated alone agree with their values inside the
+    # 1024-chain batch (not bitwise: a smaller batch uses more row chunks, i.e. another summation tree)
     lp_s, g_s = plan.logp_grad(t[:256].contiguous(), a[:256].contiguous())
-    assert torch.equal(lp_s, lp[:256]) and torch.equal(g_s, g[:256])
+    np.testing.assert_allclose(lp_s.cpu().numpy(), lp[:256].cpu().numpy(), rtol=1e-6)
+    gm = g[:256].abs().max().item()
+    np.testing.assert_allclose(g_s.cpu().numpy(), g[:256].cpu().numpy(), rtol=1e-5, atol=2e-6 * gm)
     # (3)/(4) float64 plan of the same data
     spec64, _ = synth.s3_gamlss(n=n, dtype=np.float64)
     # same float32 covariate/knots/response as the float32 model, up-cast
