@@ -222,6 +222,10 @@ int lslb_debug_set_events(void* start_event, void* stop_event);
 int lslb_debug_event_count(void);
 int lslb_debug_pipe_peak(int kind, int blocks, int iters, float* sink, double* work,
                          lslb_stream_t stream);
+/* tcgen05 building block under test: D [128 x N] = A [128 x K] . B [N x K]^T via TMA + tcgen05.mma
+ * kind::tf32 (split = 1: three-pass hi/lo split, fp32-level accuracy). N in {64,128,256}, K % 32 == 0. */
+int lslb_debug_tc_probe(const float* A, const float* B, int N, int K, int split, float* D,
+                        lslb_stream_t stream);
 
 #ifdef __cplusplus
 }

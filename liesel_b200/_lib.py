@@ -99,7 +99,11 @@ lib.lslb_debug_event_count.restype = _i
 lib.lslb_debug_pipe_peak.restype = _i
 lib.lslb_debug_pipe_peak.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_double), _vp]
 
+lib.lslb_debug_tc_probe.restype = _i
+lib.lslb_debug_tc_probe.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
+
 EXPORTS = [
+    "lslb_debug_tc_probe",
     "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
     "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
