@@ -214,6 +214,8 @@ struct lslb_plan {
   long long* d_chunk_start;  // device [nchunks+1]
   double lik_const;
   bool rows_sorted;  // every smooth's knot span changes rarely from row to row
+  float* d_XT;       // plan-owned transpose of the dense block [p x n_pad] (tensor-core path) or NULL
+  long long n_pad;
   int variant;
   const char* variant_name;
 };
@@ -242,6 +244,15 @@ LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain);
 struct BandedCfg {
   int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
 };
+struct TcCfg {
+  int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;
+};
+int dense_tc_prepare(lslb_plan* plan);                 // dense_tc.cu (called by lslb_plan_create)
+bool dense_tc_eligible(const lslb_plan* plan, int C);
+TcCfg dense_tc_cfg(const lslb_plan* plan, int C);
+size_t dense_tc_rt_floats(const lslb_plan* plan, int C);
+int launch_dense_tc(const lslb_plan* plan, const TcCfg& k, int C, const float* params, float* RT,
+                    float* partial, bool want_grad, cudaStream_t st);
 bool dgroup_x2_eligible(const lslb_plan* plan);  // dgroup_x2.cu
 LaunchCfg dgroup_x2_cfg(const lslb_plan* plan, int C);
 int launch_dgroup_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k,

@@ -1,0 +1,534 @@
+// Dense fixed-effect block on the 5th-generation tensor cores (S4: logistic regression, p = 256,
+// 1024 chains, rows sharded over GPUs). Two kernels per evaluation, both built on the block validated
+// in tc_probe.cu (TMA 128-byte-swizzled K-major tiles -> tcgen05.mma.kind::tf32 -> TMEM):
+//
+//  K1  eta^T[chains x rows] = B[chains x p] . X[rows x p]^T        (A = params, B-operand = X)
+//      epilogue (thread = chain = TMEM lane): per-row likelihood, log-lik summed in a register,
+//      residuals R^T[chain][row] written to the workspace (fp32, 128 B contiguous per thread).
+//  K2  G[p x chains] = XT[p x rows] . R^T[chains x rows]^T         (A = plan-owned transpose of X)
+//      split-K over row chunks; per-chunk partial G goes to the same partial buffer the SIMT
+//      kernels use, so finalize (fixed-order reduction + priors) is shared.
+//
+// fp32 parity (rtol 1e-5) needs more than TF32's 10-bit mantissa: every product is the 3-pass split
+//   hi(a).hi(b) + lo(a).hi(b) + hi(a).lo(b),  hi(x) = x with the low 13 mantissa bits cleared,
+// with fp32 accumulation in TMEM. hi/lo are produced in shared memory by dedicated "split" warps
+// right after a TMA tile lands (the split is element-wise, so it is blind to the swizzled layout).
+//
+// Warp roles (K1: 10 warps, K2: 6 warps), mbarrier pipelines:
+//   TMA warp  --full_raw-->  split warps  --full_split-->  MMA warp  --(commit) empty--> TMA warp
+//   K1 only:  MMA warp --(commit) tmem_full--> epilogue warps --tmem_empty--> MMA warp (2 accumulators)
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace lslb {
+
+typedef unsigned long long u64t;
+int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
+                      int box_rows);  // tc_probe.cu
+
+namespace tc {
+constexpr int KC = 32;        // K chunk in floats (one 128-byte swizzle row)
+constexpr int MT = 128;       // M tile (TMEM lanes)
+constexpr int NR1 = 256;      // K1: rows (N) per tile
+constexpr int NC2 = 128;      // K2: chains (N) per CTA
+constexpr int STAGES = 2;
+
+__device__ __forceinline__ unsigned sm(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(u64t* b, int c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sm(b)), "r"(c));
+}
+__device__ __forceinline__ void bar_expect(u64t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(u64t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm(b)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(u64t* b, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
+        : "=r"(ok)
+        : "r"(sm(b)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int c0, int c1, u64t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(sm(dst)), "l"(map), "r"(c0), "r"(c1), "r"(sm(bar))
+      : "memory");
+}
+__device__ __forceinline__ u64t desc_k_sw128(const void* smem, unsigned kbytes) {
+  const unsigned addr = sm(smem) + kbytes;
+  return (u64t)((addr >> 4) & 0x3FFF) | ((u64t)(1024 >> 4) << 32) | ((u64t)1 << 46) | ((u64t)2 << 61);
+}
+__device__ __forceinline__ unsigned idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(unsigned d, u64t a, u64t b, unsigned idesc, unsigned acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(u64t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// element-wise hi/lo split of `count` floats: hi stays in `h`, lo goes to `l`
+__device__ __forceinline__ void split_tile(float* h, float* l, int count, int t, int nthreads) {
+  for (int i = 4 * t; i < count; i += 4 * nthreads) {
+    float4 v = *reinterpret_cast<float4*>(h + i);
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(h + i) = hi;
+    *reinterpret_cast<float4*>(l + i) = lo;
+  }
+}
+
+struct Pipe {  // (stage, phase) cursor of one role
+  int s = 0;
+  unsigned ph = 0;
+  __device__ __forceinline__ void next() {
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1: eta^T tile = params tile . X tile^T, likelihood epilogue
+// ---------------------------------------------------------------------------------------------
+struct K1Stage {
+  float ah[MT * KC], al[MT * KC];    // params chunk [128 chains][32]
+  float bh[NR1 * KC], bl[NR1 * KC];  // X chunk [256 rows][32]
+};
+
+template <int FAM, bool GRAD>
+__global__ void __launch_bounds__(320, 1)
+dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX,
+            const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
+            float fixed_inv_scale, float* __restrict__ RT, float* __restrict__ partial, int Psmall, int Cpad) {
+  extern __shared__ unsigned char smraw_[];
+  unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
+  K1Stage* st = reinterpret_cast<K1Stage*>(smraw);
+  __shared__ __align__(8) u64t full_raw[STAGES], full_split[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ unsigned tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chain0 = blockIdx.x * MT;
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int my_tiles = max(0, min(tile0 + tiles_per_cta, ntiles) - tile0);
+  const int nk = p / KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      bar_init(&full_raw[s], 1);
+      bar_init(&full_split[s], 128);
+      bar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      bar_init(&tmem_full[a], 1);
+      bar_init(&tmem_empty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm(&tmem_base_s)),
+                 "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const unsigned tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      Pipe q;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int row0 = (tile0 + t) * NR1;
+        for (int kc = 0; kc < nk; ++kc) {
+          bar_wait(&empty[q.s], q.ph ^ 1);
+          bar_expect(&full_raw[q.s], (MT + NR1) * KC * 4);
+          tma2d(st[q.s].ah, &mapP, kc * KC, chain0, &full_raw[q.s]);
+          tma2d(st[q.s].bh, &mapX, kc * KC, row0, &full_raw[q.s]);
+          q.next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      Pipe q;
+      const unsigned idesc = idesc_tf32(MT, NR1);
+      for (int t = 0; t < my_tiles; ++t) {
+        const int acc = t & 1;
+        bar_wait(&tmem_empty[acc], ((t >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const unsigned d = tmem_base + (unsigned)(acc * NR1);
+        for (int kc = 0; kc < nk; ++kc) {
+          bar_wait(&full_split[q.s], q.ph);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+          for (int k8 = 0; k8 < KC / 8; ++k8) {
+            const unsigned kb = k8 * 32;
+            const u64t ah = desc_k_sw128(st[q.s].ah, kb), al = desc_k_sw128(st[q.s].al, kb);
+            const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
+            mma_tf32(d, ah, bh, idesc, (kc | k8) != 0);
+            mma_tf32(d, al, bh, idesc, 1);
+            mma_tf32(d, ah, bl, idesc, 1);
+          }
+          mma_commit(&empty[q.s]);
+          q.next();
+        }
+        mma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------- split warps (128 threads) ----------------
+    const int t128 = tid - 64;
+    Pipe q;
+    for (int t = 0; t < my_tiles; ++t) {
+      for (int kc = 0; kc < nk; ++kc) {
+        bar_wait(&full_raw[q.s], q.ph);
+        split_tile(st[q.s].ah, st[q.s].al, MT * KC, t128, 128);
+        split_tile(st[q.s].bh, st[q.s].bl, NR1 * KC, t128, 128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_arrive(&full_split[q.s]);
+        q.next();
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (128 threads): thread = TMEM lane = chain ----------------
+    const int q4 = warp & 3;               // TMEM lane quarter this warp may access
+    const int chain = chain0 + q4 * 32 + lane;
+    float lp_hi = 0.f, lp_lo = 0.f;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int acc = t & 1;
+      const long long row0 = (long long)(tile0 + t) * NR1;
+      bar_wait(&tmem_full[acc], (t >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      float lp_tile = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NR1; c0 += 32) {
+        unsigned r[32];
+        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(acc * NR1 + c0), r);
+        float dres[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const long long row = row0 + c0 + j;
+          float ll = 0.f, d0 = 0.f, d1, w0, w1;
+          if (row < n) {
+            lik_row<float, FAM, false>(__ldg(y + row), __uint_as_float(r[j]), 0.f, fixed_inv_scale, ll, d0, d1,
+                                       w0, w1);
+          }
+          lp_tile += ll;
+          dres[j] = d0;
+        }
+        if constexpr (GRAD) {
+          float4* dst = reinterpret_cast<float4*>(RT + (size_t)chain * n_pad + row0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(dres[4 * j], dres[4 * j + 1], dres[4 * j + 2], dres[4 * j + 3]);
+        }
+      }
+      kahan_add(lp_hi, lp_lo, lp_tile);
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      bar_arrive(&tmem_empty[acc]);
+    }
+    float* out = partial + (size_t)blockIdx.y * (Psmall + LSLB_NACC) * Cpad + chain;
+    out[(size_t)Psmall * Cpad] = lp_hi;
+    out[(size_t)(Psmall + 1) * Cpad] = lp_lo;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: G tile [p x 128 chains] += XT chunk . R^T chunk^T over this CTA's rows
+// ---------------------------------------------------------------------------------------------
+template <int MTILES>
+struct K2Stage {
+  float ah[MTILES][MT * KC], al[MTILES][MT * KC];  // XT chunk [128 p-rows][32 rows] per M tile
+  float bh[NC2 * KC], bl[NC2 * KC];                // R^T chunk [128 chains][32 rows]
+};
+
+template <int MTILES>
+__global__ void __launch_bounds__(192, 1)
+dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapRT, int p,
+            int kchunks_per_cta, int nkchunks, int soff, float* __restrict__ partial, int Psmall, int Cpad) {
+  extern __shared__ unsigned char smraw_[];
+  unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
+  K2Stage<MTILES>* st = reinterpret_cast<K2Stage<MTILES>*>(smraw);
+  __shared__ __align__(8) u64t full_raw[STAGES], full_split[STAGES], empty[STAGES], done;
+  __shared__ unsigned tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chain0 = blockIdx.x * NC2;
+  const int k0 = blockIdx.y * kchunks_per_cta;
+  const int my_k = max(0, min(k0 + kchunks_per_cta, nkchunks) - k0);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      bar_init(&full_raw[s], 1);
+      bar_init(&full_split[s], 128);
+      bar_init(&empty[s], 1);
+    }
+    bar_init(&done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm(&tmem_base_s)),
+                 "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const unsigned tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      Pipe q;
+      for (int kc = 0; kc < my_k; ++kc) {
+        const int r0 = (k0 + kc) * KC;
+        bar_wait(&empty[q.s], q.ph ^ 1);
+        bar_expect(&full_raw[q.s], (MTILES * MT + NC2) * KC * 4);
+#pragma unroll
+        for (int m = 0; m < MTILES; ++m) tma2d(st[q.s].ah[m], &mapXT, r0, m * MT, &full_raw[q.s]);
+        tma2d(st[q.s].bh, &mapRT, r0, chain0, &full_raw[q.s]);
+        q.next();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      Pipe q;
+      const unsigned idesc = idesc_tf32(MT, NC2);
+      for (int kc = 0; kc < my_k; ++kc) {
+        bar_wait(&full_split[q.s], q.ph);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+        for (int m = 0; m < MTILES; ++m) {
+          const unsigned d = tmem_base + (unsigned)(m * NC2);
+#pragma unroll
+          for (int k8 = 0; k8 < KC / 8; ++k8) {
+            const unsigned kb = k8 * 32;
+            const u64t ah = desc_k_sw128(st[q.s].ah[m], kb), al = desc_k_sw128(st[q.s].al[m], kb);
+            const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
+            mma_tf32(d, ah, bh, idesc, (kc | k8) != 0);
+            mma_tf32(d, al, bh, idesc, 1);
+            mma_tf32(d, ah, bl, idesc, 1);
+          }
+        }
+        mma_commit(&empty[q.s]);
+        q.next();
+      }
+      mma_commit(&done);
+    }
+  } else {
+    // split warps, then epilogue (warps 2..5 cover the four TMEM lane quarters: warp & 3 = 2,3,0,1)
+    const int t128 = tid - 64;
+    Pipe q;
+    for (int kc = 0; kc < my_k; ++kc) {
+      bar_wait(&full_raw[q.s], q.ph);
+#pragma unroll
+      for (int m = 0; m < MTILES; ++m) split_tile(st[q.s].ah[m], st[q.s].al[m], MT * KC, t128, 128);
+      split_tile(st[q.s].bh, st[q.s].bl, NC2 * KC, t128, 128);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_arrive(&full_split[q.s]);
+      q.next();
+    }
+    const int q4 = warp & 3;
+    if (my_k > 0) {
+      bar_wait(&done, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+    }
+#pragma unroll
+    for (int m = 0; m < MTILES; ++m) {
+      const int j = m * MT + q4 * 32 + lane;  // coefficient index (TMEM lane)
+      float* out = partial + ((size_t)blockIdx.y * (Psmall + LSLB_NACC) + soff + j) * Cpad + chain0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NC2; c0 += 32) {
+        unsigned r[32];
+        if (my_k > 0) {
+          tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(m * NC2 + c0), r);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
+        }
+        if (j < p) {
+          float4* dst = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            dst[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                  __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// X [n x ld] -> XT [p x n_pad] (zero padded), setup time
+__global__ void transpose_pad_kernel(const float* __restrict__ X, long long n, int p, long long ld,
+                                     long long n_pad, float* __restrict__ XT) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const long long r = r0 + k;
+    const int c = c0 + threadIdx.x;
+    tile[k][threadIdx.x] = (r < n && c < p) ? X[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int c = c0 + k;
+    const long long r = r0 + threadIdx.x;
+    if (c < p && r < n_pad) XT[(size_t)c * n_pad + r] = tile[threadIdx.x][k];
+  }
+}
+}  // namespace tc
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+bool dense_tc_structure_ok(const lslb_plan* plan) {
+  if (plan->desc.dtype != LSLB_F32) return false;
+  if (plan->ns != 0 || plan->grp >= 0 || plan->nd != 1 || plan->ni != 0 || plan->has_scale) return false;
+  const lslb_block_desc& d = plan->blk[plan->dn[0]];
+  if (d.ncoef != 128 && d.ncoef != 256) return false;
+  if ((reinterpret_cast<uintptr_t>(d.data) & 15) != 0 || (d.ld & 3) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(plan->desc.y) & 15) != 0) return false;
+  if (plan->P != d.ncoef) return false;  // params [C x P] is used directly as the K-major A operand
+  return plan->desc.n >= 32768;
+}
+
+// called from lslb_plan_create: builds the plan-owned transpose of X
+int dense_tc_prepare(lslb_plan* plan) {
+  plan->d_XT = nullptr;
+  plan->n_pad = 0;
+  if (!dense_tc_structure_ok(plan)) return LSLB_OK;
+  if (const char* e = getenv("LSLB_DISABLE_TC")) {
+    if (atoi(e) != 0) return LSLB_OK;
+  }
+  const lslb_block_desc& d = plan->blk[plan->dn[0]];
+  const long long n = plan->desc.n;
+  const long long n_pad = (n + tc::NR1 - 1) / tc::NR1 * tc::NR1;
+  float* xt = nullptr;
+  if (cudaMalloc(&xt, (size_t)d.ncoef * n_pad * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    return LSLB_OK;  // not enough memory for the transpose: the SIMT path stays in charge
+  }
+  dim3 grid((unsigned)((n_pad + 31) / 32), (d.ncoef + 31) / 32), block(32, 8);
+  tc::transpose_pad_kernel<<<grid, block>>>(reinterpret_cast<const float*>(d.data), n, d.ncoef, d.ld, n_pad, xt);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(xt);
+    return LSLB_OK;
+  }
+  plan->d_XT = xt;
+  plan->n_pad = n_pad;
+  return LSLB_OK;
+}
+
+bool dense_tc_eligible(const lslb_plan* plan, int C) { return plan->d_XT != nullptr && C >= 256; }
+
+TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
+  TcCfg k;
+  k.Cpad = (C + 127) / 128 * 128;
+  k.ntiles_chain = k.Cpad / 128;
+  const long long n_pad = plan->n_pad;
+  k.ntiles_rows = (int)(n_pad / tc::NR1);
+  k.nkchunks = (int)(n_pad / tc::KC);
+  long long want = plan->sm_count / k.ntiles_chain;
+  if (want < 1) want = 1;
+  if (want > k.ntiles_rows) want = k.ntiles_rows;
+  k.tiles_per_cta = (int)((k.ntiles_rows + want - 1) / want);
+  k.nchunks = (k.ntiles_rows + k.tiles_per_cta - 1) / k.tiles_per_cta;
+  k.kchunks_per_cta = k.tiles_per_cta * (tc::NR1 / tc::KC);
+  return k;
+}
+
+size_t dense_tc_rt_floats(const lslb_plan* plan, int C) {
+  return (size_t)((C + 127) / 128 * 128) * (size_t)plan->n_pad;
+}
+
+template <int FAM>
+static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* params, float* RT, float* partial,
+                  bool g, cudaStream_t st) {
+  const lslb_block_desc& d = plan->blk[plan->dn[0]];
+  const int p = d.ncoef;
+  const long long n = plan->desc.n, n_pad = plan->n_pad;
+  CUtensorMap mP, mX, mXT, mRT;
+  if (make_tmap_f32_k32(&mP, params, C, p, plan->P, tc::MT) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32_k32(&mX, reinterpret_cast<const float*>(d.data), n, p, d.ld, tc::NR1) != LSLB_OK)
+    return LSLB_ERR_CUDA;
+  const float fis = plan->fam == FAM_NORMAL_FIXED ? (float)(1.0 / plan->desc.fixed_scale) : 1.f;
+  const size_t smem1 = tc::STAGES * sizeof(tc::K1Stage) + 1024;
+  dim3 grid1(k.ntiles_chain, k.nchunks);
+  if (g) {
+    auto kern = tc::dense_tc_k1<FAM, true>;
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    kern<<<grid1, 320, smem1, st>>>(mP, mX, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
+                                    k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+  } else {
+    auto kern = tc::dense_tc_k1<FAM, false>;
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    kern<<<grid1, 320, smem1, st>>>(mP, mX, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
+                                    k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+  }
+  LSLB_LAUNCH_CHECK();
+  if (!g) return LSLB_OK;
+  if (make_tmap_f32_k32(&mXT, plan->d_XT, p, n_pad, n_pad, tc::MT) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32_k32(&mRT, RT, k.Cpad, n_pad, n_pad, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
+  dim3 grid2(k.ntiles_chain, k.nchunks);
+  const int soff = plan->soff[plan->dn[0]];
+  if (p == 256) {
+    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<2>) + 1024;
+    auto kern = tc::dense_tc_k2<2>;
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    kern<<<grid2, 192, smem2, st>>>(mXT, mRT, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall, k.Cpad);
+  } else {
+    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<1>) + 1024;
+    auto kern = tc::dense_tc_k2<1>;
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    kern<<<grid2, 192, smem2, st>>>(mXT, mRT, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall, k.Cpad);
+  }
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
+int launch_dense_tc(const lslb_plan* plan, const TcCfg& k, int C, const float* params, float* RT,
+                    float* partial, bool g, cudaStream_t st) {
+  switch (plan->fam) {
+    case FAM_NORMAL_FIXED: return tc_run<FAM_NORMAL_FIXED>(plan, k, C, params, RT, partial, g, st);
+    case FAM_BERNOULLI: return tc_run<FAM_BERNOULLI>(plan, k, C, params, RT, partial, g, st);
+    case FAM_POISSON: return tc_run<FAM_POISSON>(plan, k, C, params, RT, partial, g, st);
+    default: return LSLB_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace lslb

@@ -362,6 +362,16 @@ static size_t eval_smem_per_chain(const lslb_plan* plan) {
 
 // launch geometry of the logp/grad pass: the TMA run-length kernel when the plan qualifies
 static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
+  if (dense_tc_eligible(plan, C)) {
+    TcCfg t = dense_tc_cfg(plan, C);
+    LaunchCfg k;
+    k.TC = 128;
+    k.Cpad = t.Cpad;
+    k.ntiles = t.ntiles_chain;
+    k.fstride = 0;
+    k.nchunks = t.nchunks;
+    return k;
+  }
   const bool dense = dense_x2_eligible(plan);
   if (!dense && dgroup_x2_eligible(plan)) return dgroup_x2_cfg(plan, C);
   if (dense || banded_fast_eligible(plan)) {
@@ -379,7 +389,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
 
 template <typename T>
 struct WsLayout {
-  T *pT, *partial, *bT, *gbT, *gpl;
+  T *pT, *partial, *bT, *gbT, *gpl, *rt;
   int gtiles;
   size_t bytes;
 };
@@ -404,6 +414,9 @@ static WsLayout<T> layout_ws(const lslb_plan* plan, const LaunchCfg& k, void* ws
     L.gbT = take((size_t)G * k.Cpad);
     L.gpl = take((size_t)L.gtiles * k.Cpad);
   }
+  L.rt = nullptr;
+  if (plan->d_XT && k.TC == 128 && k.fstride == 0 && dense_tc_eligible(plan, k.Cpad))
+    L.rt = take(dense_tc_rt_floats(plan, k.Cpad));
   L.bytes = off;
   return L;
 }
@@ -536,11 +549,12 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (!plan || C < 1 || !params || !logp || !ws) return LSLB_ERR_INVALID;
   if (plan->A > 0 && !aux) return LSLB_ERR_INVALID;
   if ((plan->desc.dtype == LSLB_F32) != (sizeof(T) == 4)) return LSLB_ERR_INVALID;
-  const bool dense = dense_x2_eligible(plan);
-  const bool dgrp = !dense && dgroup_x2_eligible(plan);
-  const bool fast = !dense && !dgrp && banded_fast_eligible(plan);
+  const bool tcp = dense_tc_eligible(plan, C);
+  const bool dense = !tcp && dense_x2_eligible(plan);
+  const bool dgrp = !tcp && !dense && dgroup_x2_eligible(plan);
+  const bool fast = !tcp && !dense && !dgrp && banded_fast_eligible(plan);
   LaunchCfg k = eval_cfg(plan, C);
-  size_t smem = (fast || dense || dgrp) ? 0 : eval_smem_per_chain(plan) * k.TC;
+  size_t smem = (fast || dense || dgrp || tcp) ? 0 : eval_smem_per_chain(plan) * k.TC;
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -577,7 +591,10 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   const bool g = grad != nullptr;
   int st = LSLB_ERR_INVALID;
   debug_record_start(stream);
-  if (dense) {
+  if (tcp) {
+    if constexpr (sizeof(T) == 4)
+      st = launch_dense_tc(plan, dense_tc_cfg(plan, C), C, params, L.rt, L.partial, g, stream);
+  } else if (dense) {
     if constexpr (sizeof(T) == 4) st = launch_dense_x2(plan, ep, dense_x2_cfg(plan, C), g, stream);
   } else if (dgrp) {
     if constexpr (sizeof(T) == 4) st = launch_dgroup_x2(plan, ep, k, g, stream);

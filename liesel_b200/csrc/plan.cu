@@ -223,6 +223,8 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
     p->variant = VAR_GENERIC;
     p->variant_name = dense_x2_eligible(p) ? "dense_x2_register_sliced" : "generic_smem";
   }
+  dense_tc_prepare(p);
+  if (p->d_XT) p->variant_name = "dense_tcgen05_tf32x3";
   *out = p;
   return LSLB_OK;
 }
@@ -230,6 +232,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
 extern "C" void lslb_plan_destroy(lslb_plan* p) {
   if (!p) return;
   if (p->d_chunk_start) cudaFree(p->d_chunk_start);
+  if (p->d_XT) cudaFree(p->d_XT);
   delete p;
 }
 

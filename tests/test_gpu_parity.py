@@ -551,3 +551,30 @@ def test_full_size_s5_group_sum_properties(lb):
     # prior part: grad - grad_lik = -(b - m)/s^2
     pr = (g - g_l)[:, p:].double()
     np.testing.assert_allclose(pr.cpu().numpy(), (-(t[:, p:].double()) / 0.25).cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+
+# --- tensor-core dense path (tcgen05, TF32 x3 split) ------------------------------------------------
+@pytest.mark.parametrize("p,n,C", [(128, 40_000, 256), (256, 33_000, 300)])
+def test_dense_tcgen05_logistic(lb, p, n, C):
+    spec, centre = synth.s4_logistic(n=n, p=p, dtype=np.float32)
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_tcgen05_tf32x3"
+    th, aux = synth.evaluation_points(spec, centre, C)
+    sel = [0, 1, 127, 128, C - 1]
+    logp, grad = plan.logp_grad(dev(th, plan), None)
+    logp_v, _ = plan.logp_grad(dev(th, plan), None, want_grad=False)
+    torch.cuda.synchronize()
+    prep = sam.Prepared(spec)
+    ref_lp = sam.log_prob(spec, th[sel], prep=prep)
+    ref_g = sam.grad(spec, th[sel], prep=prep)
+    sc_g = sam.grad_scale(spec, th[sel], prep=prep)
+    sc_lp = sam.log_prob_scale(spec, th[sel], prep=prep)
+    lp = logp.cpu().numpy()[sel]
+    np.testing.assert_allclose(logp_v.cpu().numpy()[sel], lp, rtol=1e-6)
+    assert np.all(np.abs(lp - ref_lp) <= 1e-5 * np.abs(ref_lp) + ULPS * 2.0**-24 * sc_lp)
+    gerr = np.abs(grad.cpu().numpy()[sel] - ref_g)
+    bound = 1e-5 * np.abs(ref_g) + ULPS * 2.0**-24 * sc_g
+    assert np.all(gerr <= bound), float((gerr / bound).max())
+    # the SIMT path on the same data (fewer chains than the tensor-core threshold) agrees
+    lp_s, g_s = plan.logp_grad(dev(th[:64], plan), None)
+    np.testing.assert_allclose(lp_s.cpu().numpy(), logp.cpu().numpy()[:64], rtol=2e-6)
