@@ -112,7 +112,7 @@ __device__ __forceinline__ float fexp(float x) { return __expf(x); }
 __device__ __forceinline__ double fexp(double x) { return exp(x); }
 __device__ __forceinline__ float flog1p_pos(float e) { return __logf(1.0f + e); }  // e in (0,1]
 __device__ __forceinline__ double flog1p_pos(double e) { return log1p(e); }
-__device__ __forceinline__ float frcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }  // MUFU.RCP
 __device__ __forceinline__ double frcp(double x) { return 1.0 / x; }
 
 // internal family codes: the public enum plus "Normal with a constant scale"

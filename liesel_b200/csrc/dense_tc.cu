@@ -14,7 +14,7 @@
 // with fp32 accumulation in TMEM. hi/lo are produced in shared memory by dedicated "split" warps
 // right after a TMA tile lands (the split is element-wise, so it is blind to the swizzled layout).
 //
-// Warp roles (K1: 10 warps, K2: 6 warps), mbarrier pipelines:
+// Warp roles (K1: 14 warps, K2: 6 warps), mbarrier pipelines:
 //   TMA warp  --full_raw-->  split warps  --full_split-->  MMA warp  --(commit) empty--> TMA warp
 //   K1 only:  MMA warp --(commit) tmem_full--> epilogue warps --tmem_empty--> MMA warp (2 accumulators)
 #include <cuda.h>
@@ -105,6 +105,16 @@ __device__ __forceinline__ void split_tile(float* h, float* l, int count, int t,
   }
 }
 
+// TMA store of a [128 x 32] fp32 tile (128-byte swizzle) from shared to global memory
+__device__ __forceinline__ void tma_store2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(sm(src))
+               : "memory");
+}
+__device__ __forceinline__ void bar_named(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct Pipe {  // (stage, phase) cursor of one role
   int s = 0;
   unsigned ph = 0;
@@ -122,13 +132,14 @@ struct K1Stage {
 };
 
 template <int FAM, bool GRAD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(448, 1)
 dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX,
-            const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
+            const __grid_constant__ CUtensorMap mapRT, const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
             float fixed_inv_scale, float* __restrict__ RT, float* __restrict__ partial, int Psmall, int Cpad) {
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
   K1Stage* st = reinterpret_cast<K1Stage*>(smraw);
+  float* stage_out = reinterpret_cast<float*>(smraw + STAGES * sizeof(K1Stage));  // [128 chains][32 rows], SW128
   __shared__ __align__(8) u64t full_raw[STAGES], full_split[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -145,7 +156,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       bar_init(&tmem_full[a], 1);
-      bar_init(&tmem_empty[a], 128);
+      bar_init(&tmem_empty[a], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -217,45 +228,64 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
       }
     }
   } else {
-    // ---------------- epilogue warps (128 threads): thread = TMEM lane = chain ----------------
+    // ---------------- epilogue warps (2 x 128 threads): thread = TMEM lane = chain ----------------
+    // two warps per lane quarter; each takes one half (128 of the 256 rows) of every tile. The
+    // likelihood is evaluated branch-free for all 32 rows of a block so that the independent
+    // MUFU/FMA chains interleave (a lone warp per scheduler has only its own ILP to hide latency).
     const int q4 = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 6) >> 2;      // 0: rows 0..127 of the tile, 1: rows 128..255
+    const int first = 192 + half * 128;    // first thread of this half (issues the TMA stores)
     const int chain = chain0 + q4 * 32 + lane;
+    const int rloc = q4 * 32 + lane;       // chain within the tile = row of the staging tile
+    float* sbuf = stage_out + half * (128 * 32);
     float lp_hi = 0.f, lp_lo = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      const long long row0 = (long long)(tile0 + t) * NR1;
+      const long long row0 = (long long)(tile0 + t) * NR1 + half * 128;
       bar_wait(&tmem_full[acc], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;");
       float lp_tile = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NR1; c0 += 32) {
+      for (int c0 = 0; c0 < 128; c0 += 32) {
         unsigned r[32];
-        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(acc * NR1 + c0), r);
+        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(acc * NR1 + half * 128 + c0), r);
         float dres[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const long long row = row0 + c0 + j;
-          float ll = 0.f, d0 = 0.f, d1, w0, w1;
-          if (row < n) {
-            lik_row<float, FAM, false>(__ldg(y + row), __uint_as_float(r[j]), 0.f, fixed_inv_scale, ll, d0, d1,
-                                       w0, w1);
-          }
-          lp_tile += ll;
-          dres[j] = d0;
+          const bool valid = row < n;
+          float ll, d0, d1, w0, w1;
+          lik_row<float, FAM, false>(__ldg(y + (valid ? row : 0)), __uint_as_float(r[j]), 0.f, fixed_inv_scale,
+                                     ll, d0, d1, w0, w1);
+          lp_tile += valid ? ll : 0.f;
+          dres[j] = valid ? d0 : 0.f;
         }
         if constexpr (GRAD) {
-          float4* dst = reinterpret_cast<float4*>(RT + (size_t)chain * n_pad + row0 + c0);
+          // residual tile -> swizzled staging -> one TMA store (full 128-byte lines of R^T per chain)
+          if (tid == first) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          bar_named(1 + half, 128);         // the previous store has drained the staging buffer
+          float4* srow = reinterpret_cast<float4*>(sbuf + rloc * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(dres[4 * j], dres[4 * j + 1], dres[4 * j + 2], dres[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            srow[j ^ (rloc & 7)] = make_float4(dres[4 * j], dres[4 * j + 1], dres[4 * j + 2], dres[4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          bar_named(1 + half, 128);
+          if (tid == first) {
+            tma_store2d(&mapRT, sbuf, (int)(row0 + c0), chain0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
       kahan_add(lp_hi, lp_lo, lp_tile);
       asm volatile("tcgen05.fence::before_thread_sync;");
       bar_arrive(&tmem_empty[acc]);
     }
+    if (GRAD && tid == first) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // finalize sums (row Psmall) - (row Psmall+1): half 0 contributes +lp, half 1 contributes -(-lp)
     float* out = partial + (size_t)blockIdx.y * (Psmall + LSLB_NACC) * Cpad + chain;
-    out[(size_t)Psmall * Cpad] = lp_hi;
-    out[(size_t)(Psmall + 1) * Cpad] = lp_lo;
+    const float lp = lp_hi - lp_lo;
+    if (half == 0) out[(size_t)Psmall * Cpad] = lp;
+    else out[(size_t)(Psmall + 1) * Cpad] = -lp;
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -487,23 +517,23 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
   if (make_tmap_f32_k32(&mX, reinterpret_cast<const float*>(d.data), n, p, d.ld, tc::NR1) != LSLB_OK)
     return LSLB_ERR_CUDA;
   const float fis = plan->fam == FAM_NORMAL_FIXED ? (float)(1.0 / plan->desc.fixed_scale) : 1.f;
-  const size_t smem1 = tc::STAGES * sizeof(tc::K1Stage) + 1024;
+  const size_t smem1 = tc::STAGES * sizeof(tc::K1Stage) + 2 * 128 * 32 * 4 + 1024;
+  if (make_tmap_f32_k32(&mRT, RT, k.Cpad, n_pad, n_pad, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
   dim3 grid1(k.ntiles_chain, k.nchunks);
   if (g) {
     auto kern = tc::dense_tc_k1<FAM, true>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 320, smem1, st>>>(mP, mX, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
+    kern<<<grid1, 448, smem1, st>>>(mP, mX, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
                                     k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   } else {
     auto kern = tc::dense_tc_k1<FAM, false>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 320, smem1, st>>>(mP, mX, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
+    kern<<<grid1, 448, smem1, st>>>(mP, mX, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
                                     k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   }
   LSLB_LAUNCH_CHECK();
   if (!g) return LSLB_OK;
   if (make_tmap_f32_k32(&mXT, plan->d_XT, p, n_pad, n_pad, tc::MT) != LSLB_OK) return LSLB_ERR_CUDA;
-  if (make_tmap_f32_k32(&mRT, RT, k.Cpad, n_pad, n_pad, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
   dim3 grid2(k.ntiles_chain, k.nchunks);
   const int soff = plan->soff[plan->dn[0]];
   if (p == 256) {
