@@ -25,7 +25,10 @@
 namespace lslb {
 
 // PM: bit m set <=> smooth m feeds predictor 1 (log scale)
-template <int FAM, int NS, int PM, bool GRAD>
+// UNITY: every row's four weights sum to one (all x inside the knot range; checked at plan creation).
+// Then, over a run of equal spans, eta = b1 + sum_{u != 1} w_u (b_u - b1) and the gradient of b1 is
+// (sum of residuals) - g0 - g2 - g3: three FMAs per smooth and direction instead of four.
+template <int FAM, int NS, int PM, bool GRAD, bool UNITY>
 __global__ void __launch_bounds__(128, 4)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
   __shared__ __align__(128) XRaw<NS> raw[XSTAGES];
@@ -113,23 +116,47 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   float lpa_hi = 0.f, lpa_lo = 0.f, lpb_hi = 0.f, lpb_lo = 0.f;  // Kahan pairs, chains a and b
   u64 sr0 = pk(0.f, 0.f), sr1 = pk(0.f, 0.f);
 
-  auto change = [&](int m, int s) {
-    const int so = p.sp[m].soff;
+  bool fastmode = false;            // accumulators currently hold the 3-term (UNITY) form
+  u64 srs[NS];                      // residual-sum snapshot at the start of the current run
+  u64 e0i = o0, e1i = o1;           // predictor start values in 3-term form (offset + sum of b1)
+#pragma unroll
+  for (int m = 0; m < NS; ++m) srs[m] = pk(0.f, 0.f);
+
+  auto flush = [&](int m) {
     if constexpr (GRAD) {
       if (cur[m] >= 0) {
+        const int so = p.sp[m].soff + cur[m];
+        if (fastmode) {
+          const u64 S = add2(((PM >> m) & 1) ? sr1 : sr0, mul2(srs[m], NEG1));
+          const u64 g1 = add2(add2(S, mul2(wg[m][0], NEG1)), mul2(add2(wg[m][2], wg[m][3]), NEG1));
+          wg[m][1] = g1;
+        }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          u64* q = at2(so + cur[m] + t);
+          u64* q = at2(so + t);
           *q = add2(*q, wg[m][t]);
         }
       }
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      wb[m][t] = ld2(so + s + t);
-      wg[m][t] = pk(0.f, 0.f);
+    for (int t = 0; t < 4; ++t) wg[m][t] = pk(0.f, 0.f);
+  };
+  auto load = [&](int m, int s, bool fast) {
+    const int so = p.sp[m].soff;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) wb[m][t] = ld2(so + s + t);
+    if (fast) {
+      const u64 nb1 = mul2(wb[m][1], NEG1);
+      wb[m][0] = add2(wb[m][0], nb1);
+      wb[m][2] = add2(wb[m][2], nb1);
+      wb[m][3] = add2(wb[m][3], nb1);
     }
+    srs[m] = ((PM >> m) & 1) ? sr1 : sr0;
     cur[m] = s;
+  };
+  auto change = [&](int m, int s) {  // 4-term form (rows of a tile with mixed spans)
+    flush(m);
+    load(m, s, false);
   };
 
   for (int k = 0; k < my_tiles; ++k) {
@@ -171,15 +198,17 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
     // NR rows whose weights/responses are already in registers: forward with wb fixed across rows
     // (u-major), likelihood, backward with the residual fixed across the four weights of a row
-    auto compute_block = [&](const float (&w)[NS][4][4], const float (&yv)[4], auto NRtag) {
+    auto compute_block = [&](const float (&w)[NS][4][4], const float (&yv)[4], auto NRtag, auto FASTtag) {
       constexpr int NR = decltype(NRtag)::value;
+      constexpr bool FAST = decltype(FASTtag)::value;
       u64 eta0[NR], eta1[NR];
 #pragma unroll
-      for (int i = 0; i < NR; ++i) { eta0[i] = o0; eta1[i] = o1; }
+      for (int i = 0; i < NR; ++i) { eta0[i] = FAST ? e0i : o0; eta1[i] = FAST ? e1i : o1; }
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          if (FAST && u == 1) continue;
 #pragma unroll
           for (int i = 0; i < NR; ++i) {
             if ((PM >> m) & 1) eta1[i] = fma2(bc(w[m][i][u]), wb[m][u], eta1[i]);
@@ -217,11 +246,16 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           for (int i = 0; i < NR; ++i) {
             const u64 rr = ((PM >> m) & 1) ? d1[i] : d0[i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) wg[m][u] = fma2(bc(w[m][i][u]), rr, wg[m][u]);
+            for (int u = 0; u < 4; ++u) {
+              if (FAST && u == 1) continue;
+              wg[m][u] = fma2(bc(w[m][i][u]), rr, wg[m][u]);
+            }
           }
         }
       }
     };
+    using TFast = std::integral_constant<bool, true>;
+    using TFull = std::integral_constant<bool, false>;
     auto load_block = [&](float (&w)[NS][4][4], float (&yv)[4], int r, auto NRtag) {
       constexpr int NR = decltype(NRtag)::value;
 #pragma unroll
@@ -241,30 +275,62 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     using N1 = std::integral_constant<int, 1>;
     using N4 = std::integral_constant<int, 4>;
 
+    const bool want_fast = UNITY && uni && rows == XR;
+    if (want_fast != fastmode) {  // the accumulators change form: write them out in the old form
+#pragma unroll
+      for (int m = 0; m < NS; ++m) {
+        flush(m);
+        cur[m] = -1;
+      }
+      fastmode = want_fast;
+    }
     if (uni) {
+      bool reloaded = false;
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
         const int first = D.start[m][0];
-        if (first != cur[m]) change(m, first);
+        if (first != cur[m]) {
+          flush(m);
+          load(m, first, fastmode);
+          reloaded = true;
+        }
+      }
+      if (fastmode && reloaded) {
+        e0i = o0;
+        e1i = o1;
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+          if ((PM >> m) & 1) e1i = add2(e1i, wb[m][1]);
+          else e0i = add2(e0i, wb[m][1]);
+        }
       }
       if (rows == XR) {
         // software pipeline over 4-row blocks: the next block's weights are loaded into a second
-        // register set while the current block computes, so all operands of a block are ready
-        // together and the forward FMAs can be issued coefficient-major (operand reuse)
+        // register set while the current block computes
         float wa[NS][4][4], wbuf[NS][4][4], ya[4], yb[4];
         load_block(wa, ya, 0, N4{});
+        if (fastmode) {
 #pragma unroll 1
-        for (int r = 0; r < XR; r += 8) {
-          load_block(wbuf, yb, r + 4, N4{});
-          compute_block(wa, ya, N4{});
-          if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
-          compute_block(wbuf, yb, N4{});
+          for (int r = 0; r < XR; r += 8) {
+            load_block(wbuf, yb, r + 4, N4{});
+            compute_block(wa, ya, N4{}, TFast{});
+            if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
+            compute_block(wbuf, yb, N4{}, TFast{});
+          }
+        } else {
+#pragma unroll 1
+          for (int r = 0; r < XR; r += 8) {
+            load_block(wbuf, yb, r + 4, N4{});
+            compute_block(wa, ya, N4{}, TFull{});
+            if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
+            compute_block(wbuf, yb, N4{}, TFull{});
+          }
         }
       } else {
         float w1[NS][4][4], y1[4];
         for (int r = 0; r < rows; ++r) {
           load_block(w1, y1, r, N1{});
-          compute_block(w1, y1, N1{});
+          compute_block(w1, y1, N1{}, TFull{});
         }
       }
     } else {
@@ -276,7 +342,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           if (sm != cur[m]) change(m, sm);
         }
         load_block(w1, y1, r, N1{});
-        compute_block(w1, y1, N1{});
+        compute_block(w1, y1, N1{}, TFull{});
       }
     }
     // tile sums -> log-likelihood (row constants are added in finalize) and d/d eta1 sums
@@ -294,15 +360,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
   if constexpr (GRAD) {
 #pragma unroll
-    for (int m = 0; m < NS; ++m) {
-      if (cur[m] >= 0) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          u64* q = at2(p.sp[m].soff + cur[m] + t);
-          *q = add2(*q, wg[m][t]);
-        }
-      }
-    }
+    for (int m = 0; m < NS; ++m) flush(m);
     for (int q = 0; q < p.ni; ++q) *at2(p.ic[q].soff) = p.ic[q].pred ? sr1 : sr0;
   }
   *at2(p.Psmall) = pk(lpa_hi, lpb_hi);
@@ -311,10 +369,15 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
 // host ------------------------------------------------------------------------------------------
 template <int FAM, int NS, int PM>
-static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st) {
+static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity) {
   dim3 grid(k.ntiles_chain, k.nchunks), block(128);
-  if (g) banded_x2_kernel<FAM, NS, PM, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
-  else banded_x2_kernel<FAM, NS, PM, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+  if (unity) {
+    if (g) banded_x2_kernel<FAM, NS, PM, true, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+    else banded_x2_kernel<FAM, NS, PM, false, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+  } else {
+    if (g) banded_x2_kernel<FAM, NS, PM, true, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+    else banded_x2_kernel<FAM, NS, PM, false, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
+  }
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }
@@ -324,17 +387,17 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
   int pm = 0;
   for (int m = 0; m < plan->ns; ++m) pm |= (plan->blk[plan->sp[m]].predictor & 1) << m;
   if (plan->fam == FAM_NORMAL_LS) {
-    if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st)
-                                 : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st);
+    if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st, plan->unit_rows)
+                                 : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st, plan->unit_rows);
     switch (pm) {
-      case 0: return x2_launch<FAM_NORMAL_LS, 2, 0>(ep, k, g, st);
-      case 1: return x2_launch<FAM_NORMAL_LS, 2, 1>(ep, k, g, st);
-      case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st);
-      default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st);
+      case 0: return x2_launch<FAM_NORMAL_LS, 2, 0>(ep, k, g, st, plan->unit_rows);
+      case 1: return x2_launch<FAM_NORMAL_LS, 2, 1>(ep, k, g, st, plan->unit_rows);
+      case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st, plan->unit_rows);
+      default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st, plan->unit_rows);
     }
   }
-  if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st);
-  return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st);
+  if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st, plan->unit_rows);
+  return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st, plan->unit_rows);
 }
 
 }  // namespace lslb

@@ -214,6 +214,7 @@ struct lslb_plan {
   long long* d_chunk_start;  // device [nchunks+1]
   double lik_const;
   bool rows_sorted;  // every smooth's knot span changes rarely from row to row
+  bool unit_rows;    // every spline row's four weights sum to one (x inside the knot range)
   float* d_XT;       // plan-owned transpose of the dense block [p x n_pad] (tensor-core path) or NULL
   long long n_pad;
   int variant;

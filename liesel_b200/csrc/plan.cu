@@ -42,6 +42,24 @@ __global__ void span_changes_kernel(const int* __restrict__ start, long long n, 
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// max_i |w_i0 + w_i1 + w_i2 + w_i3 - 1| over the rows of one spline block (one block, setup time)
+template <typename T>
+__global__ void unit_rows_kernel(const T* __restrict__ w, long long n, double* out) {
+  __shared__ double sh[1024];
+  double acc = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = (double)w[4 * i] + (double)w[4 * i + 1] + (double)w[4 * i + 2] + (double)w[4 * i + 3];
+    acc = fmax(acc, fabs(s - 1.0));
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
 // sum_i lgamma(y_i + 1) in double, one block, fixed order (deterministic)
 template <typename T>
 __global__ void lgamma_sum_kernel(const T* __restrict__ y, long long n, double* out) {
@@ -201,6 +219,26 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
       for (int m = 0; m < p->ns; ++m)
         if ((long long)h[m] > n / 64 + 64) p->rows_sorted = false;
       cudaFree(d_cnt);
+    }
+  }
+  // do the four weights of every spline row sum to one? (true when all x lie inside the knot range)
+  p->unit_rows = false;
+  if (p->ns > 0 && e == cudaSuccess) {
+    double* d_mx = nullptr;
+    e = cudaMalloc(&d_mx, sizeof(double) * LSLB_MAX_SPL);
+    if (e == cudaSuccess) {
+      double h[LSLB_MAX_SPL] = {0};
+      for (int m = 0; m < p->ns; ++m) {
+        if (desc->dtype == LSLB_F32)
+          unit_rows_kernel<float><<<1, 1024>>>((const float*)p->blk[p->sp[m]].data, n, d_mx + m);
+        else
+          unit_rows_kernel<double><<<1, 1024>>>((const double*)p->blk[p->sp[m]].data, n, d_mx + m);
+      }
+      e = cudaMemcpy(h, d_mx, sizeof(double) * p->ns, cudaMemcpyDeviceToHost);
+      p->unit_rows = true;
+      for (int m = 0; m < p->ns; ++m)
+        if (!(h[m] <= (desc->dtype == LSLB_F32 ? 2e-6 : 1e-12))) p->unit_rows = false;
+      cudaFree(d_mx);
     }
   }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
