@@ -241,7 +241,7 @@ size_t workspace_bytes(const lslb_plan* plan, int C);
 struct LaunchCfg {
   int TC, Cpad, ntiles, fstride, nchunks;
 };
-LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain);
+LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain, size_t smem_fixed = 0);
 struct BandedCfg {
   int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
 };

@@ -49,11 +49,19 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int TC = blockDim.x, tid = threadIdx.x;
   const int c = blockIdx.y * TC + tid;
+  // Spline-only models (STAGED) keep only the gradient columns in shared memory and read the
+  // coefficients from the transposed copy in global memory (L1-resident): half the shared memory
+  // per chain, twice the resident warps for these latency-bound shapes.
+  constexpr bool STAGED = NS > 0 && PD == 0 && !GROUP;
   T* bs = reinterpret_cast<T*>(smraw);
-  T* gs = bs + (size_t)p.Psmall * TC;
+  T* gs = STAGED ? bs : bs + (size_t)p.Psmall * TC;
+  auto beta = [&](int j) -> T {
+    if constexpr (STAGED) return __ldg(p.pT + (size_t)j * p.Cpad + c);
+    else return bs[j * TC + tid];
+  };
 
   for (int j = 0; j < p.Psmall; ++j) {
-    bs[j * TC + tid] = p.pT[(size_t)j * p.Cpad + c];
+    if constexpr (!STAGED) bs[j * TC + tid] = p.pT[(size_t)j * p.Cpad + c];
     if constexpr (GRAD) gs[j * TC + tid] = T(0);
   }
   // every thread reads and writes only its own column of bs/gs: no barrier needed
@@ -64,7 +72,7 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 
   T o0 = T(0), o1 = T(0);
   for (int q = 0; q < p.ni; ++q) {
-    T v = bs[p.ic[q].soff * TC + tid];
+    T v = beta(p.ic[q].soff);
     if (p.ic[q].pred) o1 += v; else o0 += v;
   }
 
@@ -82,7 +90,7 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
   if constexpr (PD > 0) {
 #pragma unroll
     for (int j = 0; j < PD; ++j) {
-      bd[j] = j < p.dn[0].p ? bs[(p.dn[0].soff + j) * TC + tid] : T(0);
+      bd[j] = j < p.dn[0].p ? beta(p.dn[0].soff + j) : T(0);
       gd[j] = T(0);
     }
   }
@@ -92,8 +100,47 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 
   T lp_hi = T(0), lp_lo = T(0), sr0 = T(0), sr1 = T(0);
 
-  for (long long t0 = r0; t0 < r1; t0 += 32) {
+  // Spline-only models: the 32-row blocks of (y, start, weights) are staged in shared memory with
+  // cp.async (two stages), so the row loop never waits on global memory. Works for any alignment.
+  constexpr int NSR = NS > 0 ? NS : 1;
+  struct RowTile {
+    T w[NSR][32 * 4];
+    T y[32];
+    int start[NSR][32];
+  };
+  RowTile* tiles = reinterpret_cast<RowTile*>(
+      smraw + (((size_t)(STAGED ? 1 : 2) * p.Psmall * TC * sizeof(T)) + 15) / 16 * 16);
+  auto cp_elem = [](void* dst, const void* src, int bytes) {
+    if (bytes == 4)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    else
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  auto prefetch = [&](long long t0, int stage) {
+    if constexpr (STAGED) {
+      if (t0 < r1) {
+        const int rows = (int)(r1 - t0 < 32 ? r1 - t0 : 32);
+        RowTile& tl = tiles[stage];
+        for (int e = tid; e < rows; e += TC) cp_elem(&tl.y[e], p.y + t0 + e, sizeof(T));
+        for (int m = 0; m < p.ns; ++m) {
+          for (int e = tid; e < rows; e += TC) cp_elem(&tl.start[m][e], p.sp[m].start + t0 + e, 4);
+          for (int e = tid; e < rows * 4; e += TC) cp_elem(&tl.w[m][e], p.sp[m].w + 4 * t0 + e, sizeof(T));
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  prefetch(r0, 0);
+
+  int it = 0;
+  for (long long t0 = r0; t0 < r1; t0 += 32, ++it) {
     const long long t1 = t0 + 32 < r1 ? t0 + 32 : r1;
+    if constexpr (STAGED) {
+      prefetch(t0 + 32, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncthreads();
+    }
+    const RowTile& tl = tiles[it & 1];
     T lp_tile = T(0);
     for (long long i = t0; i < t1; ++i) {
       T eta0 = o0, eta1 = o1;
@@ -101,8 +148,14 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
         if (m < p.ns) {
-          const int s = __ldg(p.sp[m].start + i);
-          w[m] = ld4(p.sp[m].w + 4 * i);
+          int s;
+          if constexpr (STAGED) {
+            s = tl.start[m][i - t0];
+            w[m] = *reinterpret_cast<const Vec4<T>*>(&tl.w[m][4 * (i - t0)]);
+          } else {
+            s = __ldg(p.sp[m].start + i);
+            w[m] = ld4(p.sp[m].w + 4 * i);
+          }
           if (s != cur[m]) {  // warp-uniform: every lane looks at the same row
             const int so = p.sp[m].soff;
             if constexpr (GRAD) {
@@ -113,7 +166,7 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
             }
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              wb[m][t] = bs[(so + s + t) * TC + tid];
+              wb[m][t] = beta(so + s + t);
               wg[m][t] = T(0);
             }
             cur[m] = s;
@@ -158,7 +211,9 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
       }
 
       T ll, d0, d1, u0, u1;
-      lik_row<T, FAM, false>(__ldg(p.y + i), eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+      T yi;
+      if constexpr (STAGED) yi = tl.y[i - t0]; else yi = __ldg(p.y + i);
+      lik_row<T, FAM, false>(yi, eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
       lp_tile += ll;
 
       if constexpr (GRAD) {
@@ -190,6 +245,7 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
       }
     }
     kahan_add(lp_hi, lp_lo, lp_tile);
+    if constexpr (STAGED) __syncthreads();  // the stage is refilled by the next iteration's prefetch
   }
 
   // ---- flush register state and publish this chunk's partial sums ----------------------
@@ -224,9 +280,8 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 // Both finalize kernels use blocks of (32 chains) x (FIN_G helpers): helper g sums the chunk
 // partials ch = g, g + FIN_G, ... in double; the FIN_G partial sums are then combined in a fixed
 // order through shared memory, so the result does not depend on scheduling.
-constexpr int FIN_G = 8;
-
-template <typename T>
+// FIN_G is 8 for wide launches and 32 when the grid would otherwise leave most SMs idle (few chains).
+template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
 finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
                      const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad) {
@@ -265,7 +320,7 @@ finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restr
   }
 }
 
-template <typename T>
+template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
 finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
                      const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
@@ -340,13 +395,19 @@ finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restr
 // =======================================================================================
 // host side
 // =======================================================================================
-LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain) {
+LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain, size_t smem_fixed) {
   LaunchCfg k;
   k.TC = C > 64 ? 128 : (C > 32 ? 64 : 32);
   while (smem_per_chain * k.TC > 200 * 1024 && k.TC > 32) k.TC /= 2;  // many coefficients
   k.Cpad = (C + k.TC - 1) / k.TC * k.TC;
   k.ntiles = k.Cpad / k.TC;
   int ctas_per_sm = 512 / k.TC;
+  {  // resident CTAs are bounded by shared memory: size the grid to whole waves of what fits
+    size_t per_cta = smem_per_chain * k.TC + smem_fixed + 1024;
+    int fit = (int)((size_t)227 * 1024 / per_cta);
+    if (fit < 1) fit = 1;
+    if (fit < ctas_per_sm) ctas_per_sm = fit;
+  }
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles - 1) / k.ntiles;
   if (want < 1) want = 1;
   int F = plan->nchunks;
@@ -356,8 +417,18 @@ LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain) {
   return k;
 }
 
+// spline-only plans run the staged form of eval_kernel: gradient columns only + two row stages
+static bool eval_staged(const lslb_plan* plan) {
+  return plan->variant == VAR_BANDED;
+}
 static size_t eval_smem_per_chain(const lslb_plan* plan) {
-  return (size_t)2 * plan->Psmall * (plan->desc.dtype == LSLB_F32 ? 4 : 8);
+  return (size_t)(eval_staged(plan) ? 1 : 2) * plan->Psmall * (plan->desc.dtype == LSLB_F32 ? 4 : 8);
+}
+static size_t eval_smem_fixed(const lslb_plan* plan) {
+  if (!eval_staged(plan)) return 0;
+  const size_t ts = plan->desc.dtype == LSLB_F32 ? 4 : 8;
+  const int NS = plan->ns <= 1 ? 1 : (plan->ns <= 3 ? plan->ns : (plan->ns <= 5 ? 5 : 8));  // dispatch_structure
+  return 16 + 2 * ((size_t)NS * (128 * ts + 128) + 32 * ts);
 }
 
 // launch geometry of the logp/grad pass: the TMA run-length kernel when the plan qualifies
@@ -384,7 +455,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
     k.nchunks = b.nchunks;
     return k;
   }
-  return choose_cfg(plan, C, eval_smem_per_chain(plan));
+  return choose_cfg(plan, C, eval_smem_per_chain(plan), eval_smem_fixed(plan));
 }
 
 template <typename T>
@@ -554,7 +625,7 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   const bool dgrp = !tcp && !dense && dgroup_x2_eligible(plan);
   const bool fast = !tcp && !dense && !dgrp && banded_fast_eligible(plan);
   LaunchCfg k = eval_cfg(plan, C);
-  size_t smem = (fast || dense || dgrp || tcp) ? 0 : eval_smem_per_chain(plan) * k.TC;
+  size_t smem = (fast || dense || dgrp || tcp) ? 0 : eval_smem_per_chain(plan) * k.TC + eval_smem_fixed(plan);
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -613,8 +684,11 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (g) {
     long long total = (long long)plan->Psmall * k.Cpad;
     if (total > 0) {
-      dim3 fgrid(k.Cpad / 32, plan->Psmall), fblock(32, FIN_G);
-      finalize_grad_kernel<T><<<fgrid, fblock, 0, stream>>>(fp, L.partial, L.pT, aux, grad);
+      dim3 fgrid(k.Cpad / 32, plan->Psmall);
+      if ((long long)fgrid.x * fgrid.y < 4LL * plan->sm_count)
+        finalize_grad_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad);
+      else
+        finalize_grad_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad);
       LSLB_LAUNCH_CHECK();
     }
     if (plan->grp >= 0) {
@@ -624,8 +698,8 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
       LSLB_LAUNCH_CHECK();
     }
   }
-  finalize_logp_kernel<T><<<k.Cpad / 32, dim3(32, FIN_G), 0, stream>>>(fp, L.partial, L.pT, aux,
-                                                                       L.gpl, L.gtiles, G, logp);
+  finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
+                                                                        L.gpl, L.gtiles, G, logp);
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }
