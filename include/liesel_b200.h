@@ -97,6 +97,10 @@ typedef struct lslb_block_desc {
   double tau2_fixed;
   double ig_a;
   double ig_b;
+  const void* center; /* spline: column means cbar[ncoef] (model dtype) or NULL. When set the term
+                         is the column-centred basis (B - 1 cbar^T) beta, i.e. the dense centred
+                         design matrix a Liesel user passes to add_np_smooth for identifiability,
+                         kept in banded form plus a rank-one correction. */
 } lslb_block_desc;
 
 typedef struct lslb_model_desc {

@@ -36,6 +36,7 @@ class BlockDesc(C.Structure):
         ("rank", C.c_double), ("log_pdet", C.c_double),
         ("tau2_slot", C.c_int32), ("has_ig", C.c_int32),
         ("tau2_fixed", C.c_double), ("ig_a", C.c_double), ("ig_b", C.c_double),
+        ("center", C.c_void_p),
     ]
 
 

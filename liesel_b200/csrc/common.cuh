@@ -8,7 +8,7 @@
 
 #define LSLB_MAX_SPL 8
 #define LSLB_MAX_DNS 4
-#define LSLB_MAX_INT 4
+#define LSLB_MAX_INT 6  // 4 intercept blocks + one virtual row per predictor (centred splines)
 #define LSLB_NACC 2  // extra accumulator rows per chunk: logp (hi, lo)
 
 namespace lslb {
@@ -72,6 +72,8 @@ struct PriorP {
   double rank, log_pdet, tau2_fixed, ig_a, ig_b, ig_const;  // ig_const = a log b - lgamma(a)
   int tau2_slot;
   int has_ig;
+  int vrow;            // small-space row of the predictor's centring term (-1: block not centred)
+  const void* center;  // column means of a centred spline block
 };
 
 template <typename T>
@@ -101,6 +103,7 @@ struct FinalizeParams {
   int nblocks;
   PriorP pr[LSLB_MAX_BLOCKS];
   int P, A, Psmall, C, Cpad, nchunks;
+  int Preal;  // rows [Preal, Psmall) of the small space are virtual (centring terms)
   double lik_const, const_term;
   unsigned flags;
 };
@@ -203,7 +206,9 @@ struct lslb_plan {
   lslb_block_desc blk[LSLB_MAX_BLOCKS];
   int soff[LSLB_MAX_BLOCKS];  // small-space offsets (-1 for the group block)
   int off[LSLB_MAX_BLOCKS];   // flat offsets
-  int P, A, Psmall;
+  int P, A, Psmall;  // Psmall counts the virtual centring rows; Preal does not
+  int Preal;
+  int vrow[2];       // per predictor: small-space row holding -sum_b cbar_b^T beta_b, or -1
   int ns, nd, ni;
   int sp[LSLB_MAX_SPL], dn[LSLB_MAX_DNS], ic[LSLB_MAX_INT];
   int grp;  // index of the group block or -1

@@ -178,12 +178,28 @@ iwls_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ Iwl
   for (int j = 0; j < q.nq; ++j) out[(size_t)j * p.Cpad] = as[j * TC + tid];
 }
 
-// score [C x p], info [C x p x p] from the chunk partials + prior terms
+// Sums the chunk partials into chunk 0 (each thread owns one (row, chain) column, fixed order).
+// Used before the finalize step of a centred spline block, whose correction needs whole sums.
+template <typename T>
+__global__ void iwls_reduce_kernel(T* partial, int nq, int Cpad, int nchunks) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)nq * Cpad;
+  if (idx >= stride) return;
+  double acc = 0.0;
+  for (int ch = 0; ch < nchunks; ++ch) acc += (double)partial[ch * stride + idx];
+  partial[idx] = (T)acc;
+}
+
+// score [C x p], info [C x p x p] from the chunk partials + prior terms.
+// center != NULL (spline target with column-centred basis, rows summing to one, fp.nchunks == 1):
+// with s = B^T r, G = B^T W B banded, u = G 1 = B^T W 1, Omega = 1^T u, R = 1^T s
+//   score = s - cbar R,   info = G - cbar u^T - u cbar^T + Omega cbar cbar^T.
 template <typename T>
 __global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, int block, int tkind,
                                      int p, int nq, const T* __restrict__ partial,
                                      const T* __restrict__ pT, const T* __restrict__ aux,
-                                     T* __restrict__ score, T* __restrict__ info) {
+                                     T* __restrict__ score, T* __restrict__ info,
+                                     const T* __restrict__ center) {
   // thread per (entry e in [0, p + p*p), chain c); c fastest for coalesced partial reads
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ne = p + p * p;
@@ -197,10 +213,25 @@ __global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, 
   if (pr.prior == LSLB_PRIOR_MVND)
     tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)c * fp.A + pr.tau2_slot] : pr.tau2_fixed;
   const size_t stride = (size_t)nq * fp.Cpad;
+  auto red = [&](int row) { return (double)partial[(size_t)row * fp.Cpad + c]; };
+  auto gram = [&](int i, int j) {  // banded entry of the reduced Gram (centred case)
+    const int lo = i < j ? i : j, d = i < j ? j - i : i - j;
+    return d < 4 ? red(p + 4 * lo + d) : 0.0;
+  };
+  auto usum = [&](int i) {
+    double u = 0.0;
+    for (int l = (i > 3 ? i - 3 : 0); l <= (i + 3 < p ? i + 3 : p - 1); ++l) u += gram(i, l);
+    return u;
+  };
   if (e < p) {
     double acc = 0.0;
     const T* src = partial + (size_t)e * fp.Cpad + c;
     for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+    if (center) {
+      double R = 0.0;
+      for (int j = 0; j < p; ++j) R += red(j);
+      acc -= (double)center[e] * R;
+    }
     if (with_prior) {
       if (pr.prior == LSLB_PRIOR_NORMAL) {
         acc -= ((double)pT[(size_t)(pr.soff + e) * fp.Cpad + c] - pr.m) * pr.inv_s2;
@@ -228,6 +259,13 @@ __global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, 
   if (row >= 0) {
     const T* src = partial + (size_t)row * fp.Cpad + c;
     for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+  }
+  if (center) {
+    double omega = 0.0;
+    for (int i = 0; i < p; ++i) omega += usum(i);
+    // canonical (a <= b) operand order: entries (i, j) and (j, i) are bitwise equal
+    const double ca = (double)center[a], cb = (double)center[b];
+    acc += -ca * usum(b) - usum(a) * cb + ca * cb * omega;
   }
   if (with_prior) {
     if (pr.prior == LSLB_PRIOR_NORMAL) {
@@ -546,6 +584,8 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
   if (!iwls_target(plan, block, tkind, tidx)) return LSLB_ERR_UNSUPPORTED;
   const int p = plan->blk[block].ncoef;
   if (p > LSLB_MAX_IWLS_P) return LSLB_ERR_UNSUPPORTED;
+  // the centring correction of the target block uses u = G 1, which needs basis rows summing to one
+  if (plan->blk[block].center && !plan->unit_rows) return LSLB_ERR_UNSUPPORTED;
   const int nq = iwls_nq(tkind, p);
   const bool fast = iwls_fast(plan, tkind);
   LaunchCfg k = iwls_cfg(plan, C, tkind, nq);
@@ -597,8 +637,16 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
   debug_record_stop(stream);
   if (st != LSLB_OK) return st;
   long long ne = (long long)(p + p * p) * k.Cpad;
+  const T* center = reinterpret_cast<const T*>(plan->blk[block].center);
+  if (center) {
+    long long nr = (long long)nq * k.Cpad;
+    iwls_reduce_kernel<T><<<(unsigned)((nr + 255) / 256), 256, 0, stream>>>(L.partial, nq, k.Cpad,
+                                                                            k.nchunks);
+    LSLB_LAUNCH_CHECK();
+    fp.nchunks = 1;
+  }
   iwls_finalize_kernel<T><<<(unsigned)((ne + 255) / 256), 256, 0, stream>>>(
-      fp, block, tkind, p, nq, L.partial, L.pT, aux, score, info);
+      fp, block, tkind, p, nq, L.partial, L.pT, aux, score, info, center);
   LSLB_LAUNCH_CHECK();
   if (chol) return launch_chol<T>(C, p, info, chol, stream);
   return LSLB_OK;

@@ -284,7 +284,8 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
 finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
-                     const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad) {
+                     const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
+                     T* __restrict__ vsum) {
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y;
@@ -299,6 +300,10 @@ finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restr
   acc = 0.0;
 #pragma unroll
   for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
+  if (j >= fp.Preal) {  // residual sum of a predictor with centred splines: used by center_fix_kernel
+    vsum[(size_t)(j - fp.Preal) * fp.Cpad + c] = (T)acc;
+    return;
+  }
   for (int b = 0; b < fp.nblocks; ++b) {
     const PriorP& pr = fp.pr[b];
     if (pr.soff < 0 || j < pr.soff || j >= pr.soff + pr.ncoef) continue;
@@ -318,6 +323,21 @@ finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restr
     grad[(size_t)c * fp.P + pr.off + jj] = (T)acc;
     break;
   }
+}
+
+// grad[c, block] -= cbar * (residual sum of the block's predictor): the rank-one part of
+// (B - 1 cbar^T)^T r for centred spline blocks. Thread per (coefficient of a centred block, chain).
+template <typename T>
+__global__ void center_fix_kernel(const __grid_constant__ FinalizeParams fp,
+                                  const T* __restrict__ vsum, T* __restrict__ grad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  const PriorP& pr = fp.pr[b];
+  if (c >= fp.C || pr.vrow < 0) return;
+  const T R = vsum[(size_t)(pr.vrow - fp.Preal) * fp.Cpad + c];
+  const T* cb = reinterpret_cast<const T*>(pr.center);
+  T* g = grad + (size_t)c * fp.P + pr.off;
+  for (int t = 0; t < pr.ncoef; ++t) g[t] -= cb[t] * R;
 }
 
 template <typename T, int FIN_G>
@@ -460,7 +480,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
 
 template <typename T>
 struct WsLayout {
-  T *pT, *partial, *bT, *gbT, *gpl, *rt;
+  T *pT, *partial, *bT, *gbT, *gpl, *rt, *vsum;
   int gtiles;
   size_t bytes;
 };
@@ -476,6 +496,7 @@ static WsLayout<T> layout_ws(const lslb_plan* plan, const LaunchCfg& k, void* ws
   };
   L.pT = take((size_t)plan->Psmall * k.Cpad);
   L.partial = take((size_t)k.nchunks * (plan->Psmall + LSLB_NACC) * k.Cpad);
+  L.vsum = take((size_t)2 * k.Cpad);  // residual sums of the (at most two) centring rows
   L.gtiles = 0;
   L.bT = L.gbT = L.gpl = nullptr;
   if (plan->grp >= 0) {
@@ -525,7 +546,10 @@ void fill_finalize_params(const lslb_plan* plan, FinalizeParams& fp, int C, int 
     pr.ig_const = d.has_ig ? d.ig_a * log(d.ig_b) - lgamma(d.ig_a) : 0.0;
     pr.tau2_slot = d.tau2_slot;
     pr.has_ig = d.has_ig;
+    pr.vrow = d.center ? plan->vrow[d.predictor] : -1;
+    pr.center = d.center;
   }
+  fp.Preal = plan->Preal;
   fp.P = plan->P;
   fp.A = plan->A;
   fp.Psmall = plan->Psmall;
@@ -557,6 +581,8 @@ void fill_eval_params(const lslb_plan* plan, EvalParams<T>& ep, int C, int Cpad)
   }
   for (int m = 0; m < plan->ni; ++m)
     ep.ic[m] = {plan->soff[plan->ic[m]], plan->blk[plan->ic[m]].predictor};
+  for (int k = 0; k < 2; ++k)  // centring terms enter as one more intercept per predictor
+    if (plan->vrow[k] >= 0) ep.ic[ep.ni++] = {plan->vrow[k], k};
   ep.gidx = nullptr;
   ep.gpred = 0;
   ep.G = 0;
@@ -686,9 +712,14 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
     if (total > 0) {
       dim3 fgrid(k.Cpad / 32, plan->Psmall);
       if ((long long)fgrid.x * fgrid.y < 4LL * plan->sm_count)
-        finalize_grad_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad);
+        finalize_grad_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum);
       else
-        finalize_grad_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad);
+        finalize_grad_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum);
+      LSLB_LAUNCH_CHECK();
+      if (plan->Psmall > plan->Preal) {
+        dim3 cgrid((C + 127) / 128, plan->desc.nblocks);
+        center_fix_kernel<T><<<cgrid, 128, 0, stream>>>(fp, L.vsum, grad);
+      }
       LSLB_LAUNCH_CHECK();
     }
     if (plan->grp >= 0) {

@@ -131,11 +131,12 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
         else p->grp = b;
         break;
       case LSLB_INTERCEPT:
-        if (d.ncoef != 1 || p->ni >= LSLB_MAX_INT) bad = true;
+        if (d.ncoef != 1 || p->ni >= LSLB_MAX_INT - 2) bad = true;
         else p->ic[p->ni++] = b;
         break;
       default: bad = true;
     }
+    if (d.center && d.kind != LSLB_SPLINE) bad = true;
     if (bad) {
       delete p;
       return LSLB_ERR_INVALID;
@@ -153,6 +154,13 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   }
   p->desc.blocks = p->blk;
   p->P = off;
+  p->Preal = soff;
+  // centred spline blocks: (B - 1 cbar^T) beta = B beta + v with v = -cbar^T beta constant over the
+  // rows, so each predictor gets ONE virtual intercept row; its gradient (the residual sum) is
+  // folded back into the blocks' gradients by the finalize step.
+  p->vrow[0] = p->vrow[1] = -1;
+  for (int b = 0; b < desc->nblocks; ++b)
+    if (p->blk[b].center && p->vrow[p->blk[b].predictor] < 0) p->vrow[p->blk[b].predictor] = soff++;
   p->Psmall = soff;
   p->A = aux;
   p->fam = desc->family == LSLB_NORMAL ? (p->has_scale ? FAM_NORMAL_LS : FAM_NORMAL_FIXED)

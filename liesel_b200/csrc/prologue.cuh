@@ -16,7 +16,17 @@ __global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
   int c = (int)(idx % fp.Cpad);
   int j = (int)(idx / fp.Cpad);
   T v = T(0);
-  if (c < fp.C) {
+  if (c < fp.C && j >= fp.Preal) {  // virtual row: minus the centring terms of this predictor
+    double acc = 0.0;
+    for (int b = 0; b < fp.nblocks; ++b) {
+      const PriorP& pr = fp.pr[b];
+      if (pr.vrow != j) continue;
+      const T* cb = reinterpret_cast<const T*>(pr.center);
+      const T* x = params + (long long)c * fp.P + pr.off;
+      for (int t = 0; t < pr.ncoef; ++t) acc += (double)cb[t] * (double)x[t];
+    }
+    v = (T)(-acc);
+  } else if (c < fp.C) {
     for (int b = 0; b < fp.nblocks; ++b) {
       const PriorP& pr = fp.pr[b];
       if (pr.soff >= 0 && j >= pr.soff && j < pr.soff + pr.ncoef) {

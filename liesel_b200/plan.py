@@ -78,13 +78,24 @@ class Plan:
                 d = blocks[b]
                 d.kind, d.predictor, d.ncoef = blk.kind, blk.predictor, blk.ncoef
                 d.data, d.index, d.ld, d.K = None, None, 0, None
-                d.tau2_slot, d.has_ig = -1, 0
+                d.tau2_slot, d.has_ig, d.center = -1, 0, None
                 if blk.kind == KIND_DENSE:
                     d.data = rows[f"X{b}"].data_ptr()
                     d.ld = rows[f"X{b}"].shape[1]
                 elif blk.kind == KIND_SPLINE:
                     d.data = rows[f"w{b}"].data_ptr()
                     d.index = rows[f"s{b}"].data_ptr()
+                    if blk.center:
+                        if blk.colmean is None:  # column means of the basis, accumulated in fp64
+                            w64 = rows[f"w{b}"].to(torch.float64)
+                            cols = rows[f"s{b}"].to(torch.int64)[:, None] + torch.arange(
+                                w64.shape[1], device=dev)[None, :]
+                            cm = torch.zeros(blk.ncoef, dtype=torch.float64, device=dev)
+                            cm.index_add_(0, cols.reshape(-1), w64.reshape(-1))
+                            blk.colmean = (cm / max(y.numel(), 1)).cpu().numpy().astype(spec.dtype)
+                        cmt = torch.as_tensor(np.asarray(blk.colmean), device=dev).to(dt).contiguous()
+                        self._keep.append(cmt)
+                        d.center = cmt.data_ptr()
                 elif blk.kind == KIND_GROUP:
                     d.index = rows[f"g{b}"].data_ptr()
                 pr = blk.prior

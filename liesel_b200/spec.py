@@ -87,6 +87,10 @@ class Block:
     order: int = 3
     start: np.ndarray | None = None  # int32 [n], first non-zero basis column
     weights: np.ndarray | None = None  # [n, order+1]
+    # spline: column-centred design B - 1 colmean^T (colmean filled by Plan when center is True
+    # and no array was given)
+    center: bool = False
+    colmean: np.ndarray | None = None
     # group
     idx: np.ndarray | None = None  # int32 [n], sorted ascending
     # filled by ModelSpec
@@ -202,11 +206,18 @@ class ModelSpec:
         self, x, knots, K, a: float | None, b: float | None, predictor: str, name: str,
         order: int = 3, tau2_name: str | None = "auto", tau2_init: float = 10000.0,
         start: np.ndarray | None = None, weights: np.ndarray | None = None,
+        center: bool | np.ndarray = False,
     ) -> "ModelSpec":
         """
         ``add_np_smooth`` whose design matrix is ``basis_matrix(x, knots, order)``
         (reference ``contrib/splines.py:109-198``), kept in banded form: per row the first
         non-zero column ``start`` and ``order + 1`` weights.
+
+        ``center``: the design matrix is the column-centred basis ``B - 1 cbar^T`` (what a Liesel
+        user passes to ``add_np_smooth`` so that the smooth is identified next to an intercept).
+        ``True`` takes ``cbar`` = column means of ``B`` (computed when the plan is built and stored
+        in ``Block.colmean``); an array of ``k`` values is used as given. The band stays sparse;
+        the rank-one part is handled in closed form.
         """
         pred = self._check_predictor(predictor)
         self._check_name(name)
@@ -219,6 +230,12 @@ class ModelSpec:
             raise ValueError("either x or a precomputed (start, weights) band is required")
         prior = self._mvnd_prior(K, a, b, name, tau2_name, tau2_init) if K is not None else None
         blk = Block(name, KIND_SPLINE, pred, k, prior, x=x, knots=knots, order=order)
+        if isinstance(center, np.ndarray):
+            if center.shape != (k,):
+                raise ValueError("center must have one entry per basis function")
+            blk.center, blk.colmean = True, np.ascontiguousarray(center, dtype=self.dtype)
+        else:
+            blk.center = bool(center)
         if start is not None:
             blk.start = np.ascontiguousarray(start, dtype=np.int32)
             blk.weights = np.ascontiguousarray(weights, dtype=self.dtype)

@@ -41,7 +41,10 @@ def s1_blr(n: int = 1000, p: int = 10, dtype=np.float32, seed: int = 101):
 
 def s2_pspline_gam(n: int = 100_000, n_smooth: int = 5, k: int = 20, dtype=np.float32,
                    seed: int = 102):
-    """S2: additive model with n_smooth cubic P-splines, sigma fixed at 0.5, tau2 ~ IG(1, 0.005)."""
+    """
+    S2: additive model with n_smooth cubic P-splines, sigma fixed at 0.5, tau2 ~ IG(1, 0.005).
+    Each basis is column-centred (B - 1 cbar^T) so that the smooths do not absorb a level.
+    """
     rng = np.random.default_rng(seed)
     xs = rng.uniform(size=(n_smooth, n))
     f = sum(np.sin(2 * np.pi * xs[j] * (j + 1) / 2) for j in range(n_smooth))
@@ -54,12 +57,14 @@ def s2_pspline_gam(n: int = 100_000, n_smooth: int = 5, k: int = 20, dtype=np.fl
     for j in range(n_smooth):
         xj = xs[j].astype(dtype)
         knots = equidistant_knots(xj, k, 3)
-        spec.add_spline_smooth(xj, knots, K, 1.0, 0.005, "loc", f"loc_np{j}", tau2_init=1.0)
+        spec.add_spline_smooth(xj, knots, K, 1.0, 0.005, "loc", f"loc_np{j}", tau2_init=1.0,
+                               center=True)
         centre.append(np.sin(2 * np.pi * _greville(knots.astype(np.float64)) * (j + 1) / 2))
     return spec, np.concatenate(centre)
 
 
-def s3_gamlss(n: int = 1_000_000, k: int = 20, dtype=np.float32, seed: int = 103):
+def s3_gamlss(n: int = 1_000_000, k: int = 20, dtype=np.float32, seed: int = 103,
+              center: bool = False):
     """
     S3 / H: Gaussian location-scale model; mean and log-sd are each intercept + cubic
     P-spline of the same covariate. Block order: loc_p0, loc_np0, scale_p0, scale_np0
@@ -76,9 +81,10 @@ def s3_gamlss(n: int = 1_000_000, k: int = 20, dtype=np.float32, seed: int = 103
     xd = x.astype(dtype)
     knots = equidistant_knots(xd, k, 3)
     spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, "loc", "loc_p0")
-    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "loc", "loc_np0", tau2_init=1.0)
+    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "loc", "loc_np0", tau2_init=1.0, center=center)
     spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, "scale", "scale_p0")
-    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "scale", "scale_np0", tau2_init=1.0)
+    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "scale", "scale_np0", tau2_init=1.0,
+                           center=center)
     g = _greville(knots.astype(np.float64))
     centre = np.concatenate([[1.0], np.sin(2 * np.pi * g), [-0.5], 0.5 * np.cos(2 * np.pi * g)])
     return spec, centre

@@ -58,6 +58,15 @@ class Prepared:
                 ent["start"] = start.astype(np.int64)
                 ent["w"] = w.astype(self.dt)
                 ent["cols"] = ent["start"][:, None] + np.arange(w.shape[1])[None, :]
+                # column-centred design B - 1 cbar^T (the dense matrix a user hands to
+                # add_np_smooth, distreg.py:175); cbar as stored in the spec, else the column
+                # means of B in fp64 rounded to the data dtype like every other data array
+                if getattr(blk, "center", False):
+                    cm = getattr(blk, "colmean", None)
+                    if cm is None:
+                        cm = S.band_to_dense(ent["start"], np.asarray(w, dtype=np.float64),
+                                             blk.ncoef).mean(axis=0).astype(np.asarray(w).dtype)
+                    ent["cbar"] = np.asarray(cm, dtype=self.dt)
             elif blk.kind == KIND_GROUP:
                 ent["idx"] = np.asarray(blk.idx, dtype=np.int64)
             self.blocks.append(ent)
@@ -68,7 +77,10 @@ class Prepared:
         if blk.kind == KIND_DENSE:
             return ent["X"] @ beta  # jnp.dot(X, beta), distreg.py:105,175
         if blk.kind == KIND_SPLINE:
-            return np.sum(ent["w"] * beta[ent["cols"]], axis=1)
+            eta = np.sum(ent["w"] * beta[ent["cols"]], axis=1)
+            if "cbar" in ent:
+                eta = eta - ent["cbar"] @ beta
+            return eta
         if blk.kind == KIND_INTERCEPT:
             return np.full(self.n, beta[0], dtype=self.dt)  # jnp.dot(ones[n,1], beta)
         return beta[ent["idx"]]  # b[idx], SURVEY a14
@@ -81,6 +93,8 @@ class Prepared:
         if blk.kind == KIND_SPLINE:
             out = np.zeros(blk.ncoef, dtype=self.dt)
             np.add.at(out, ent["cols"].ravel(), (ent["w"] * r[:, None]).ravel())
+            if "cbar" in ent:
+                out = out - ent["cbar"] * r.sum()
             return out
         if blk.kind == KIND_INTERCEPT:
             return np.array([r.sum()], dtype=self.dt)
@@ -91,7 +105,8 @@ class Prepared:
         if blk.kind == KIND_DENSE:
             return ent["X"]
         if blk.kind == KIND_SPLINE:
-            return S.band_to_dense(ent["start"], ent["w"], blk.ncoef)
+            B = S.band_to_dense(ent["start"], ent["w"], blk.ncoef)
+            return B - ent["cbar"][None, :] if "cbar" in ent else B
         if blk.kind == KIND_INTERCEPT:
             return np.ones((self.n, 1), dtype=self.dt)
         raise ValueError("no dense design for group blocks")
@@ -315,6 +330,8 @@ def grad_scale(spec, params, aux=None, prep=None):
             elif blk.kind == KIND_SPLINE:
                 g = np.zeros(blk.ncoef)
                 np.add.at(g, ent["cols"].ravel(), (np.abs(ent["w"]) * r[:, None]).ravel())
+                if "cbar" in ent:
+                    g = g + np.abs(ent["cbar"]) * r.sum()
             elif blk.kind == KIND_INTERCEPT:
                 g = np.array([r.sum()])
             else:

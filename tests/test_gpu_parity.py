@@ -46,6 +46,7 @@ def make(cfg, dtype):
         "s1": lambda: synth.s1_blr(n=1000, dtype=dtype),
         "s2": lambda: synth.s2_pspline_gam(n=20_000, dtype=dtype),
         "s3": lambda: synth.s3_gamlss(n=50_000, dtype=dtype),
+        "s3c": lambda: synth.s3_gamlss(n=50_000, dtype=dtype, center=True),
         "s4": lambda: synth.s4_logistic(n=4000, p=48, dtype=dtype),
         "s4s": lambda: synth.s4_logistic(n=4000, p=12, dtype=dtype),
         "s5": lambda: synth.s5_poisson_ri(n=20_000, G=500, dtype=dtype),
@@ -87,6 +88,20 @@ def test_logp_grad_parity(lb, cfg, dtype):
     C = {"s1": 4, "s2": 64, "s3": 40, "s4": 12, "s5": 33, "s5u": 7}[cfg]
     th, aux = synth.evaluation_points(spec, centre, C)
     check_logp_grad(spec, plan, th, aux)
+
+
+@pytest.mark.parametrize("C", [24, 300])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_centred_splines(lb, C, dtype):
+    """Column-centred bases (B - 1 cbar^T) in both predictors: the scalar kernels (C = 24, fp64)
+    and the packed kernel (fp32, C > 128), log-prob/gradient and the IWLS quantities."""
+    spec, centre = make("s3c", dtype)
+    plan = lb.Plan(spec)
+    assert spec.block("loc_np0").colmean is not None
+    th, aux = synth.evaluation_points(spec, centre, C, tau2="loguniform")
+    check_logp_grad(spec, plan, th, aux, chains=None if C < 100 else [0, 1, 127, 128, 255, 299])
+    for name in ["loc_p0", "loc_np0", "scale_np0"]:
+        check_iwls(spec, plan, name, th, aux, chains=[0, 1, 2, C // 2, C - 1])
 
 
 @pytest.mark.parametrize("tau2", ["start", "loguniform"])
@@ -182,11 +197,14 @@ def test_group_index_passthrough(lb):
 
 
 # --- IWLS ---------------------------------------------------------------------------------
-def check_iwls(spec, plan, block, th, aux):
+def check_iwls(spec, plan, block, th, aux, chains=None):
     dt = np.dtype(spec.dtype)
     score, info, chol = plan.iwls(block, dev(th, plan), dev(aux, plan) if spec.num_aux else None)
     torch.cuda.synchronize()
     score, info, chol = score.cpu().numpy(), info.cpu().numpy(), chol.cpu().numpy()
+    if chains is not None:  # device call on all chains, oracle on a subset
+        sel = np.asarray(chains)
+        score, info, chol, th, aux = score[sel], info[sel], chol[sel], th[sel], aux[sel]
     prep = sam.Prepared(spec)
     r_score, r_info = sam.iwls(spec, block, th, aux, prep=prep)
     blk = spec.block(block)

@@ -310,3 +310,47 @@ def test_tau2_gibbs_params():
     K = spec.blocks[0].prior.K
     assert a == pytest.approx(1.0 + 0.5 * 6)
     np.testing.assert_allclose(b, 0.005 + 0.5 * np.einsum("ci,ij,cj->c", th, K, th))
+
+
+def test_centred_spline_equals_dense_centred_design():
+    """
+    The oracle's closed form for a column-centred basis (band + rank-one term) equals the plain
+    dense path ``jnp.dot(X, beta)`` (distreg.py:175) with X = B - 1 cbar^T, for value, gradient
+    and the IWLS quantities.
+    """
+    from liesel_b200.spec import ModelSpec
+    from liesel_b200.splines import equidistant_knots, pspline_penalty
+
+    rng = np.random.default_rng(5)
+    n, k = 400, 9
+    x = rng.uniform(size=n)
+    y = np.sin(3 * x) + rng.normal(scale=0.3, size=n)
+    knots = equidistant_knots(x, k, 3)
+    K = pspline_penalty(k, 2)
+    start, w = OS.banded_basis(x, knots, 3)
+    B = OS.band_to_dense(start, w, k)
+    cbar = B.mean(axis=0)
+
+    def build(dense):
+        spec = ModelSpec(dtype=np.dtype(np.float64))
+        spec.add_response(y, "normal").add_predictor("loc").add_predictor("scale")
+        spec.add_p_smooth(np.ones((n, 1)), 0.0, 10.0, "loc", "loc_p0")
+        if dense:
+            spec.add_np_smooth(B - cbar[None, :], K, 1.0, 0.005, "loc", "loc_np0")
+        else:
+            spec.add_spline_smooth(x, knots, K, 1.0, 0.005, "loc", "loc_np0", start=start,
+                                   weights=w, center=cbar)
+        spec.add_p_smooth(np.ones((n, 1)), 0.0, 10.0, "scale", "scale_p0")
+        return spec
+
+    a, b = build(False), build(True)
+    th = rng.normal(scale=0.3, size=(3, a.num_params))
+    aux = np.exp(rng.normal(size=(3, a.num_aux)))
+    np.testing.assert_allclose(sam.log_prob(a, th, aux), sam.log_prob(b, th, aux), rtol=1e-12)
+    np.testing.assert_allclose(sam.grad(a, th, aux), sam.grad(b, th, aux), rtol=1e-9, atol=1e-9)
+    sa, ia = sam.iwls(a, "loc_np0", th, aux)
+    sb, ib = sam.iwls(b, "loc_np0", th, aux)
+    np.testing.assert_allclose(sa, sb, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(ia, ib, rtol=1e-9, atol=1e-9)
+    # centred columns sum to zero over the rows: the constant direction is not identified
+    assert np.abs((B - cbar).sum(axis=0)).max() < 1e-10
