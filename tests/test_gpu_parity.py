@@ -596,3 +596,18 @@ def test_dense_tcgen05_logistic(lb, p, n, C):
     # the SIMT path on the same data (fewer chains than the tensor-core threshold) agrees
     lp_s, g_s = plan.logp_grad(dev(th[:64], plan), None)
     np.testing.assert_allclose(lp_s.cpu().numpy(), logp.cpu().numpy()[:64], rtol=2e-6)
+
+
+def test_device_diagnostics_on_gpu(lb):
+    """Bulk-ESS and split-R-hat computed on the GPU that stores the draws equal the host versions."""
+    from liesel_b200 import diagnostics
+
+    rng = np.random.default_rng(11)
+    n, c, P = 300, 16, 4
+    x = np.zeros((n, c, P))
+    e = rng.normal(size=(n, c, P))
+    for t in range(1, n):
+        x[t] = 0.6 * x[t - 1] + e[t]
+    t = torch.as_tensor(x, device="cuda")
+    np.testing.assert_allclose(diagnostics.ess_bulk_device(t), diagnostics.ess_bulk(x), rtol=1e-8)
+    np.testing.assert_allclose(diagnostics.split_rhat_device(t), diagnostics.split_rhat(x), rtol=1e-8)

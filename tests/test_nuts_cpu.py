@@ -99,3 +99,20 @@ def test_nuts_recovers_model_lm(golden_dir):
     assert acc == pytest.approx(0.8, abs=0.05)
     codes = np.concatenate([i.error_code.numpy() for i in infos])
     assert (codes == 0).mean() > 0.98
+
+
+def test_device_diagnostics_match_host_versions():
+    """The torch (device) bulk-ESS / split-R-hat are the same algorithm as the NumPy ones."""
+    rng = np.random.default_rng(3)
+    n, c, P = 400, 6, 3
+    x = np.zeros((n, c, P))
+    e = rng.normal(size=(n, c, P))
+    for t in range(1, n):
+        x[t] = 0.8 * x[t - 1] + e[t]
+    x[:, :, 1] = np.round(x[:, :, 1], 1)  # ties: average ranks
+    x[:, 0, 2] += 2.5  # one chain elsewhere: R-hat well above 1
+    t = torch.as_tensor(x)
+    np.testing.assert_allclose(diagnostics.ess_bulk_device(t), diagnostics.ess_bulk(x), rtol=1e-9)
+    r = diagnostics.split_rhat(x)
+    np.testing.assert_allclose(diagnostics.split_rhat_device(t), r, rtol=1e-9)
+    assert r[0] < 1.05 and r[2] > 1.1

@@ -90,8 +90,8 @@ def functional_ess(d):
     from oracle_free_basis import probe_design
 
     Bp = probe_design(spec)  # [npred][10, P]
-    vals = np.concatenate([d @ B.T for B in Bp], axis=2)  # [draws, chains, 20]
-    return diagnostics.ess_bulk(vals)
+    vals = torch.cat([d.double() @ torch.as_tensor(B, device=d.device).T for B in Bp], dim=2)  # [draws, chains, 20]
+    return diagnostics.ess_bulk_device(vals)
 
 
 q0 = torch.as_tensor(th0, device=dev)
@@ -106,8 +106,8 @@ if args.sampler == "iwls":
     draws, _, infos = smp.sample(args.samples)
     sync()
     t2 = time.perf_counter()
-    ess = diagnostics.ess_bulk(draws.cpu().numpy())
-    ess_f = functional_ess(draws.cpu().numpy())
+    ess = diagnostics.ess_bulk_device(draws)
+    ess_f = functional_ess(draws)
     acc = {b.name: float(np.mean([float(i[b.name]["acceptance_prob"].mean()) for i in infos])) for b in smp.blocks}
     print(json.dumps({
         "model": "S3", "sampler": "IWLS blocks + Gibbs tau2", "n": args.n, "chains": C, "arm": "b200",
@@ -131,10 +131,13 @@ ev_w = s.evals
 draws, infos = s.sample(args.samples, hook=gibbs)
 sync()
 t2 = time.perf_counter()
-d = draws.cpu().numpy()
-ess = diagnostics.ess_bulk(d)
-ess_f = functional_ess(d)
+td = time.perf_counter()
+ess = diagnostics.ess_bulk_device(draws)  # on the device that stores the chains (cpu arm: host)
+ess_f = functional_ess(draws)
+rhat = diagnostics.split_rhat_device(draws)
+sync()
 out = {
+    "split_rhat_max": float(rhat.max()), "diagnostics_seconds": time.perf_counter() - td,
     "ess_bulk_min_identified_functionals": float(ess_f.min()),
     "ess_per_sec_posterior_identified": float(ess_f.min() / (t2 - t1)),
     "model": "S3/H", "n": args.n, "chains": C, "P": int(q0.shape[1]), "arm": "cpu_port" if args.cpu else "b200",
