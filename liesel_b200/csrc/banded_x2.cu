@@ -99,6 +99,9 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     const u64 v = ld2(p.ic[q].soff);
     if (p.ic[q].pred) o1 = add2(o1, v); else o0 = add2(o0, v);
   }
+  // Normal location-scale: predictor 1 is carried as -log2(e) * eta1 (its coefficients are scaled
+  // once when a run starts), so exp(-eta1) is a bare ex2 with no per-row multiply
+  if constexpr (FAM == FAM_NORMAL_LS) o1 = mul2(o1, pk(-1.4426950408889634f, -1.4426950408889634f));
   if constexpr (GRAD) {
     for (int j = 0; j < p.Psmall; ++j) *at2(j) = pk(0.f, 0.f);
   }
@@ -145,6 +148,12 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     const int so = p.sp[m].soff;
 #pragma unroll
     for (int t = 0; t < 4; ++t) wb[m][t] = ld2(so + s + t);
+    if constexpr (FAM == FAM_NORMAL_LS) {
+      if ((PM >> m) & 1) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) wb[m][t] = mul2(wb[m][t], NLOG2E);
+      }
+    }
     if (fast) {
       const u64 nb1 = mul2(wb[m][1], NEG1);
       wb[m][0] = add2(wb[m][0], nb1);
@@ -222,9 +231,8 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
         const u64 d = fma2(eta0[i], NEG1, bc(yv[i]));  // y - eta0
         u64 inv_s;
         if constexpr (FAM == FAM_NORMAL_LS) {
-          const u64 tt = mul2(eta1[i], NLOG2E);
           float ta, tb;
-          upk(tt, ta, tb);
+          upk(eta1[i], ta, tb);  // already -log2(e) * eta1
           inv_s = pk(ex2f(ta), ex2f(tb));  // exp(-eta1)
           se1 = add2(se1, eta1[i]);
         } else {
@@ -349,6 +357,10 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     float z2a, z2b, e1a, e1b;
     upk(sz2, z2a, z2b);
     upk(se1, e1a, e1b);
+    if constexpr (FAM == FAM_NORMAL_LS) {  // se1 holds -log2(e) * sum eta1
+      e1a *= -0.6931471805599453f;
+      e1b *= -0.6931471805599453f;
+    }
     kahan_add(lpa_hi, lpa_lo, fmaf(-0.5f, z2a, -e1a));
     kahan_add(lpb_hi, lpb_lo, fmaf(-0.5f, z2b, -e1b));
     if constexpr (GRAD && FAM == FAM_NORMAL_LS) {
