@@ -227,7 +227,8 @@ int lslb_debug_event_count(void);
 int lslb_debug_pipe_peak(int kind, int blocks, int iters, float* sink, double* work,
                          lslb_stream_t stream);
 /* tcgen05 building block under test: D [128 x N] = A [128 x K] . B [N x K]^T via TMA + tcgen05.mma
- * kind::tf32 (split = 1: three-pass hi/lo split, fp32-level accuracy). N in {64,128,256}, K % 32 == 0. */
+ * kind::tf32 (split bit 0: three-pass hi/lo split, fp32-level accuracy; bit 1: K chunks of 16 floats
+ * with the 64-byte swizzle instead of 32 floats with the 128-byte swizzle). N in {64,128,256}, K % 32 == 0. */
 int lslb_debug_tc_probe(const float* A, const float* B, int N, int K, int split, float* D,
                         lslb_stream_t stream);
 

@@ -220,7 +220,8 @@ struct lslb_plan {
   double lik_const;
   bool rows_sorted;  // every smooth's knot span changes rarely from row to row
   bool unit_rows;    // every spline row's four weights sum to one (x inside the knot range)
-  float* d_XT;       // plan-owned transpose of the dense block [p x n_pad] (tensor-core path) or NULL
+  float* d_XT;       // tensor-core path (or NULL): plan-owned hi part of the transposed dense block [p x n_pad]
+  float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
   long long n_pad;
   int variant;
   const char* variant_name;
@@ -254,6 +255,7 @@ struct TcCfg {
   int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;
 };
 int dense_tc_prepare(lslb_plan* plan);                 // dense_tc.cu (called by lslb_plan_create)
+void dense_tc_release(lslb_plan* plan);
 bool dense_tc_eligible(const lslb_plan* plan, int C);
 TcCfg dense_tc_cfg(const lslb_plan* plan, int C);
 size_t dense_tc_rt_floats(const lslb_plan* plan, int C);

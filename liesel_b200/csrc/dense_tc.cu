@@ -5,18 +5,23 @@
 //  K1  eta^T[chains x rows] = B[chains x p] . X[rows x p]^T        (A = params, B-operand = X)
 //      epilogue (thread = chain = TMEM lane): per-row likelihood, log-lik summed in a register,
 //      residuals R^T[chain][row] written to the workspace (fp32, 128 B contiguous per thread).
-//  K2  G[p x chains] = XT[p x rows] . R^T[chains x rows]^T         (A = plan-owned transpose of X)
+//  K2  G^T[chains x p] = R^T[chains x rows] . XT[p x rows]^T       (A = residuals, B-operand = XT)
 //      split-K over row chunks; per-chunk partial G goes to the same partial buffer the SIMT
 //      kernels use, so finalize (fixed-order reduction + priors) is shared.
 //
 // fp32 parity (rtol 1e-5) needs more than TF32's 10-bit mantissa: every product is the 3-pass split
 //   hi(a).hi(b) + lo(a).hi(b) + hi(a).lo(b),  hi(x) = x with the low 13 mantissa bits cleared,
-// with fp32 accumulation in TMEM. hi/lo are produced in shared memory by dedicated "split" warps
-// right after a TMA tile lands (the split is element-wise, so it is blind to the swizzled layout).
+// with fp32 accumulation in TMEM. Both kernels are bound by SHARED-MEMORY bandwidth, not by the
+// tensor pipe (per 32-wide K chunk the MMAs read 144 KB of operands for ~1600 tensor cycles, and
+// every byte an on-the-fly split reads and writes comes on top), so the constant operands are split
+// ONCE: the plan owns X_hi/X_lo and XT_hi/XT_lo, the coefficients are split by a small pre-kernel
+// per call, and only the residual tile of K2 (produced by K1 a moment earlier) is split in shared
+// memory by dedicated warps (element-wise, hence blind to the swizzled layout).
 //
-// Warp roles (K1: 14 warps, K2: 6 warps), mbarrier pipelines:
-//   TMA warp  --full_raw-->  split warps  --full_split-->  MMA warp  --(commit) empty--> TMA warp
-//   K1 only:  MMA warp --(commit) tmem_full--> epilogue warps --tmem_empty--> MMA warp (2 accumulators)
+// Warp roles, mbarrier pipelines:
+//   K1 (10 warps): TMA warp --full--> MMA warp --(commit) empty--> TMA warp;
+//                  MMA warp --(commit) tmem_full--> 8 epilogue warps --tmem_empty--> MMA warp (2 accumulators)
+//   K2 (6 warps):  TMA warp --full_raw--> 4 split warps --full_split--> MMA warp --(commit) empty--> TMA warp
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -27,9 +32,12 @@ namespace lslb {
 typedef unsigned long long u64t;
 int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
                       int box_rows);  // tc_probe.cu
+int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                  int kc);
 
 namespace tc {
-constexpr int KC = 32;        // K chunk in floats (one 128-byte swizzle row)
+constexpr int KC = 32;        // K chunk in floats: one 64-byte swizzle row (48 KB stages, 4 in flight:
+                              // the loads come from DRAM and two 96 KB stages could not cover its latency)
 constexpr int MT = 128;       // M tile (TMEM lanes)
 constexpr int NR1 = 256;      // K1: rows (N) per tile
 constexpr int NC2 = 128;      // K2: chains (N) per CTA
@@ -61,9 +69,12 @@ __device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int c0,
       ::"r"(sm(dst)), "l"(map), "r"(c0), "r"(c1), "r"(sm(bar))
       : "memory");
 }
+// K-major operand tile with rows of KC floats = one swizzle row: SBO = 8 rows, layout SWIZZLE_128B (2)
+// for 128-byte rows, SWIZZLE_64B (4) for 64-byte rows (validated stand-alone in tc_probe.cu)
 __device__ __forceinline__ u64t desc_k_sw128(const void* smem, unsigned kbytes) {
   const unsigned addr = sm(smem) + kbytes;
-  return (u64t)((addr >> 4) & 0x3FFF) | ((u64t)(1024 >> 4) << 32) | ((u64t)1 << 46) | ((u64t)2 << 61);
+  return (u64t)((addr >> 4) & 0x3FFF) | ((u64t)((8 * KC * 4) >> 4) << 32) | ((u64t)1 << 46) |
+         ((u64t)(KC == 32 ? 2 : 4) << 61);
 }
 __device__ __forceinline__ unsigned idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
@@ -132,15 +143,16 @@ struct K1Stage {
 };
 
 template <int FAM, bool GRAD>
-__global__ void __launch_bounds__(448, 1)
-dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapX,
+__global__ void __launch_bounds__(320, 1)
+dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
+            const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
             const __grid_constant__ CUtensorMap mapRT, const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
             float fixed_inv_scale, float* __restrict__ RT, float* __restrict__ partial, int Psmall, int Cpad) {
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
   K1Stage* st = reinterpret_cast<K1Stage*>(smraw);
   float* stage_out = reinterpret_cast<float*>(smraw + STAGES * sizeof(K1Stage));  // [128 chains][32 rows], SW128
-  __shared__ __align__(8) u64t full_raw[STAGES], full_split[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) u64t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chain0 = blockIdx.x * MT;
@@ -150,8 +162,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      bar_init(&full_raw[s], 1);
-      bar_init(&full_split[s], 128);
+      bar_init(&full[s], 1);
       bar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -178,9 +189,11 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
         const int row0 = (tile0 + t) * NR1;
         for (int kc = 0; kc < nk; ++kc) {
           bar_wait(&empty[q.s], q.ph ^ 1);
-          bar_expect(&full_raw[q.s], (MT + NR1) * KC * 4);
-          tma2d(st[q.s].ah, &mapP, kc * KC, chain0, &full_raw[q.s]);
-          tma2d(st[q.s].bh, &mapX, kc * KC, row0, &full_raw[q.s]);
+          bar_expect(&full[q.s], 2 * (MT + NR1) * KC * 4);
+          tma2d(st[q.s].ah, &mapPh, kc * KC, chain0, &full[q.s]);
+          tma2d(st[q.s].al, &mapPl, kc * KC, chain0, &full[q.s]);
+          tma2d(st[q.s].bh, &mapXh, kc * KC, row0, &full[q.s]);
+          tma2d(st[q.s].bl, &mapXl, kc * KC, row0, &full[q.s]);
           q.next();
         }
       }
@@ -196,7 +209,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
         asm volatile("tcgen05.fence::after_thread_sync;");
         const unsigned d = tmem_base + (unsigned)(acc * NR1);
         for (int kc = 0; kc < nk; ++kc) {
-          bar_wait(&full_split[q.s], q.ph);
+          bar_wait(&full[q.s], q.ph);
           asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
           for (int k8 = 0; k8 < KC / 8; ++k8) {
@@ -213,28 +226,14 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
         mma_commit(&tmem_full[acc]);
       }
     }
-  } else if (warp < 6) {
-    // ---------------- split warps (128 threads) ----------------
-    const int t128 = tid - 64;
-    Pipe q;
-    for (int t = 0; t < my_tiles; ++t) {
-      for (int kc = 0; kc < nk; ++kc) {
-        bar_wait(&full_raw[q.s], q.ph);
-        split_tile(st[q.s].ah, st[q.s].al, MT * KC, t128, 128);
-        split_tile(st[q.s].bh, st[q.s].bl, NR1 * KC, t128, 128);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        bar_arrive(&full_split[q.s]);
-        q.next();
-      }
-    }
   } else {
     // ---------------- epilogue warps (2 x 128 threads): thread = TMEM lane = chain ----------------
     // two warps per lane quarter; each takes one half (128 of the 256 rows) of every tile. The
     // likelihood is evaluated branch-free for all 32 rows of a block so that the independent
     // MUFU/FMA chains interleave (a lone warp per scheduler has only its own ILP to hide latency).
     const int q4 = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 6) >> 2;      // 0: rows 0..127 of the tile, 1: rows 128..255
-    const int first = 192 + half * 128;    // first thread of this half (issues the TMA stores)
+    const int half = (warp - 2) >> 2;      // 0: rows 0..127 of the tile, 1: rows 128..255
+    const int first = 64 + half * 128;     // first thread of this half (issues the TMA stores)
     const int chain = chain0 + q4 * 32 + lane;
     const int rloc = q4 * 32 + lane;       // chain within the tile = row of the staging tile
     float* sbuf = stage_out + half * (128 * 32);
@@ -271,7 +270,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           bar_named(1 + half, 128);
           if (tid == first) {
-            tma_store2d(&mapRT, sbuf, (int)(row0 + c0), chain0);
+            tma_store2d(&mapRT, sbuf, 0, (int)((row0 + c0) / 32) * Cpad + chain0);  // blocked R^T: [row/32][chain][32]
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -297,19 +296,20 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------
 // K2: G tile [p x 128 chains] += XT chunk . R^T chunk^T over this CTA's rows
 // ---------------------------------------------------------------------------------------------
-template <int MTILES>
+template <int NP>
 struct K2Stage {
-  float ah[MTILES][MT * KC], al[MTILES][MT * KC];  // XT chunk [128 p-rows][32 rows] per M tile
-  float bh[NC2 * KC], bl[NC2 * KC];                // R^T chunk [128 chains][32 rows]
+  float ah[NC2 * KC], al[NC2 * KC];  // R^T chunk [128 chains][32 rows]: raw -> hi, lo (split here)
+  float bh[NP * KC], bl[NP * KC];    // XT chunk [NP coefficients][32 rows], pre-split by the plan
 };
 
-template <int MTILES>
+template <int NP>
 __global__ void __launch_bounds__(192, 1)
-dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ CUtensorMap mapRT, int p,
-            int kchunks_per_cta, int nkchunks, int soff, float* __restrict__ partial, int Psmall, int Cpad) {
+dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ CUtensorMap mapXTl,
+            const __grid_constant__ CUtensorMap mapRT, int p, int kchunks_per_cta, int nkchunks, int soff,
+            float* __restrict__ partial, int Psmall, int Cpad) {
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
-  K2Stage<MTILES>* st = reinterpret_cast<K2Stage<MTILES>*>(smraw);
+  K2Stage<NP>* st = reinterpret_cast<K2Stage<NP>*>(smraw);
   __shared__ __align__(8) u64t full_raw[STAGES], full_split[STAGES], empty[STAGES], done;
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -328,7 +328,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ C
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm(&tmem_base_s)),
-                 "r"(256));
+                 "r"(NP));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -342,32 +342,28 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ C
       for (int kc = 0; kc < my_k; ++kc) {
         const int r0 = (k0 + kc) * KC;
         bar_wait(&empty[q.s], q.ph ^ 1);
-        bar_expect(&full_raw[q.s], (MTILES * MT + NC2) * KC * 4);
-#pragma unroll
-        for (int m = 0; m < MTILES; ++m) tma2d(st[q.s].ah[m], &mapXT, r0, m * MT, &full_raw[q.s]);
-        tma2d(st[q.s].bh, &mapRT, r0, chain0, &full_raw[q.s]);
+        bar_expect(&full_raw[q.s], (NC2 + 2 * NP) * KC * 4);
+        tma2d(st[q.s].ah, &mapRT, r0 % 32, (r0 / 32) * Cpad + chain0, &full_raw[q.s]);
+        tma2d(st[q.s].bh, &mapXTh, 0, (k0 + kc) * p, &full_raw[q.s]);
+        tma2d(st[q.s].bl, &mapXTl, 0, (k0 + kc) * p, &full_raw[q.s]);
         q.next();
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       Pipe q;
-      const unsigned idesc = idesc_tf32(MT, NC2);
+      const unsigned idesc = idesc_tf32(NC2, NP);
       for (int kc = 0; kc < my_k; ++kc) {
         bar_wait(&full_split[q.s], q.ph);
         asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-        for (int m = 0; m < MTILES; ++m) {
-          const unsigned d = tmem_base + (unsigned)(m * NC2);
-#pragma unroll
-          for (int k8 = 0; k8 < KC / 8; ++k8) {
-            const unsigned kb = k8 * 32;
-            const u64t ah = desc_k_sw128(st[q.s].ah[m], kb), al = desc_k_sw128(st[q.s].al[m], kb);
-            const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
-            mma_tf32(d, ah, bh, idesc, (kc | k8) != 0);
-            mma_tf32(d, al, bh, idesc, 1);
-            mma_tf32(d, ah, bl, idesc, 1);
-          }
+        for (int k8 = 0; k8 < KC / 8; ++k8) {
+          const unsigned kb = k8 * 32;
+          const u64t ah = desc_k_sw128(st[q.s].ah, kb), al = desc_k_sw128(st[q.s].al, kb);
+          const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
+          mma_tf32(tmem_base, ah, bh, idesc, (kc | k8) != 0);
+          mma_tf32(tmem_base, al, bh, idesc, 1);
+          mma_tf32(tmem_base, ah, bl, idesc, 1);
         }
         mma_commit(&empty[q.s]);
         q.next();
@@ -375,14 +371,13 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ C
       mma_commit(&done);
     }
   } else {
-    // split warps, then epilogue (warps 2..5 cover the four TMEM lane quarters: warp & 3 = 2,3,0,1)
+    // split warps (residual tile only), then epilogue: warps 2..5 cover the four TMEM lane
+    // quarters (warp & 3 = 2,3,0,1); thread = chain, columns = coefficients
     const int t128 = tid - 64;
     Pipe q;
     for (int kc = 0; kc < my_k; ++kc) {
       bar_wait(&full_raw[q.s], q.ph);
-#pragma unroll
-      for (int m = 0; m < MTILES; ++m) split_tile(st[q.s].ah[m], st[q.s].al[m], MT * KC, t128, 128);
-      split_tile(st[q.s].bh, st[q.s].bl, NC2 * KC, t128, 128);
+      split_tile(st[q.s].ah, st[q.s].al, NC2 * KC, t128, 128);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bar_arrive(&full_split[q.s]);
       q.next();
@@ -392,39 +387,59 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXT, const __grid_constant__ C
       bar_wait(&done, 0);
       asm volatile("tcgen05.fence::after_thread_sync;");
     }
-#pragma unroll
-    for (int m = 0; m < MTILES; ++m) {
-      const int j = m * MT + q4 * 32 + lane;  // coefficient index (TMEM lane)
-      float* out = partial + ((size_t)blockIdx.y * (Psmall + LSLB_NACC) + soff + j) * Cpad + chain0;
+    float* out = partial + ((size_t)blockIdx.y * (Psmall + LSLB_NACC) + soff) * Cpad + chain0 + q4 * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NC2; c0 += 32) {
-        unsigned r[32];
-        if (my_k > 0) {
-          tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(m * NC2 + c0), r);
-        } else {
+    for (int c0 = 0; c0 < NP; c0 += 32) {
+      unsigned r[32];
+      if (my_k > 0) {
+        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)c0, r);
+      } else {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
-        }
-        if (j < p) {
-          float4* dst = reinterpret_cast<float4*>(out + c0);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj)
-            dst[jj] = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
-                                  __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
-        }
+        for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
       }
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        if (c0 + jj < p) out[(size_t)(c0 + jj) * Cpad] = __uint_as_float(r[jj]);  // 128 B per warp store
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NP));
   }
 }
 
-// X [n x ld] -> XT [p x n_pad] (zero padded), setup time
-__global__ void transpose_pad_kernel(const float* __restrict__ X, long long n, int p, long long ld,
-                                     long long n_pad, float* __restrict__ XT) {
+// hi/lo split of a row-major matrix, setup time: hi may alias src
+__global__ void split_matrix_kernel(const float* __restrict__ src, long long rows, int cols, long long ld_src,
+                                    long long ld_dst, float* hi, float* lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i % cols);
+  const float v = src[r * ld_src + c];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[r * ld_dst + c] = h;
+  lo[r * ld_dst + c] = v - h;
+}
+
+// params [C x P] -> Ph, Pl [Cpad x p] (rows >= C zero), per call
+__global__ void split_params_kernel(const float* __restrict__ params, int C, int Cpad, int P, int p,
+                                    float* __restrict__ ph, float* __restrict__ pl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cpad * p) return;
+  const int c = i / p, j = i % p;
+  const float v = c < C ? params[(size_t)c * P + j] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  ph[i] = h;
+  pl[i] = v - h;
+}
+
+// X [n x ld] -> chunk-blocked transpose, split into hi/lo (setup time):
+//   dst[((r / KC) * p + j) * KC + r % KC] = X[r][j]   (rows r >= n are zero)
+// so that the [p x KC] tile of one K chunk is ONE contiguous block of global memory (a TMA box over
+// the plain [p x n_pad] transpose would gather 64..128-byte pieces 4*n_pad bytes apart).
+__global__ void transpose_block_split_kernel(const float* __restrict__ X, long long n, int p, long long ld,
+                                             long long n_pad, float* __restrict__ hi, float* __restrict__ lo) {
   __shared__ float tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -437,7 +452,13 @@ __global__ void transpose_pad_kernel(const float* __restrict__ X, long long n, i
   for (int k = threadIdx.y; k < 32; k += 8) {
     const int c = c0 + k;
     const long long r = r0 + threadIdx.x;
-    if (c < p && r < n_pad) XT[(size_t)c * n_pad + r] = tile[threadIdx.x][k];
+    if (c < p && r < n_pad) {
+      const float v = tile[threadIdx.x][k];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const size_t d = ((size_t)(r / KC) * p + c) * KC + (size_t)(r % KC);
+      hi[d] = h;
+      lo[d] = v - h;
+    }
   }
 }
 }  // namespace tc
@@ -456,9 +477,18 @@ bool dense_tc_structure_ok(const lslb_plan* plan) {
   return plan->desc.n >= 32768;
 }
 
-// called from lslb_plan_create: builds the plan-owned transpose of X
+// called from lslb_plan_create: builds the plan-owned, pre-split copies X_hi/X_lo [n x p] and
+// XT_hi/XT_lo [p x n_pad] (4x the bytes of X; when they do not fit, the SIMT path stays in charge)
+void dense_tc_release(lslb_plan* plan) {
+  if (plan->d_XT) cudaFree(plan->d_XT);
+  if (plan->d_XTl) cudaFree(plan->d_XTl);
+  if (plan->d_Xh) cudaFree(plan->d_Xh);
+  if (plan->d_Xl) cudaFree(plan->d_Xl);
+  plan->d_XT = plan->d_XTl = plan->d_Xh = plan->d_Xl = nullptr;
+}
+
 int dense_tc_prepare(lslb_plan* plan) {
-  plan->d_XT = nullptr;
+  plan->d_XT = plan->d_XTl = plan->d_Xh = plan->d_Xl = nullptr;
   plan->n_pad = 0;
   if (!dense_tc_structure_ok(plan)) return LSLB_OK;
   if (const char* e = getenv("LSLB_DISABLE_TC")) {
@@ -466,20 +496,25 @@ int dense_tc_prepare(lslb_plan* plan) {
   }
   const lslb_block_desc& d = plan->blk[plan->dn[0]];
   const long long n = plan->desc.n;
+  const int p = d.ncoef;
   const long long n_pad = (n + tc::NR1 - 1) / tc::NR1 * tc::NR1;
-  float* xt = nullptr;
-  if (cudaMalloc(&xt, (size_t)d.ncoef * n_pad * sizeof(float)) != cudaSuccess) {
+  const size_t bt = (size_t)p * n_pad * sizeof(float), bx = (size_t)n * p * sizeof(float);
+  if (cudaMalloc(&plan->d_XT, bt) != cudaSuccess || cudaMalloc(&plan->d_XTl, bt) != cudaSuccess ||
+      cudaMalloc(&plan->d_Xh, bx) != cudaSuccess || cudaMalloc(&plan->d_Xl, bx) != cudaSuccess) {
     cudaGetLastError();
-    return LSLB_OK;  // not enough memory for the transpose: the SIMT path stays in charge
-  }
-  dim3 grid((unsigned)((n_pad + 31) / 32), (d.ncoef + 31) / 32), block(32, 8);
-  tc::transpose_pad_kernel<<<grid, block>>>(reinterpret_cast<const float*>(d.data), n, d.ncoef, d.ld, n_pad, xt);
-  if (cudaDeviceSynchronize() != cudaSuccess) {
-    cudaGetLastError();
-    cudaFree(xt);
+    dense_tc_release(plan);
     return LSLB_OK;
   }
-  plan->d_XT = xt;
+  const float* X = reinterpret_cast<const float*>(d.data);
+  dim3 grid((unsigned)((n_pad + 31) / 32), (p + 31) / 32), block(32, 8);
+  tc::transpose_block_split_kernel<<<grid, block>>>(X, n, p, d.ld, n_pad, plan->d_XT, plan->d_XTl);
+  const long long ex = n * p;
+  tc::split_matrix_kernel<<<(unsigned)((ex + 255) / 256), 256>>>(X, n, p, d.ld, p, plan->d_Xh, plan->d_Xl);
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    dense_tc_release(plan);
+    return LSLB_OK;
+  }
   plan->n_pad = n_pad;
   return LSLB_OK;
 }
@@ -502,8 +537,10 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
   return k;
 }
 
+// workspace of the tensor-core path: R^T [Cpad x n_pad] + the split coefficients 2 x [Cpad x p]
 size_t dense_tc_rt_floats(const lslb_plan* plan, int C) {
-  return (size_t)((C + 127) / 128 * 128) * (size_t)plan->n_pad;
+  const size_t Cpad = (size_t)((C + 127) / 128 * 128);
+  return Cpad * (size_t)plan->n_pad + 2 * Cpad * (size_t)plan->blk[plan->dn[0]].ncoef;
 }
 
 template <int FAM>
@@ -512,40 +549,52 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
   const lslb_block_desc& d = plan->blk[plan->dn[0]];
   const int p = d.ncoef;
   const long long n = plan->desc.n, n_pad = plan->n_pad;
-  CUtensorMap mP, mX, mXT, mRT;
-  if (make_tmap_f32_k32(&mP, params, C, p, plan->P, tc::MT) != LSLB_OK) return LSLB_ERR_CUDA;
-  if (make_tmap_f32_k32(&mX, reinterpret_cast<const float*>(d.data), n, p, d.ld, tc::NR1) != LSLB_OK)
-    return LSLB_ERR_CUDA;
+  CUtensorMap mPh, mPl, mXh, mXl, mXTh, mXTl, mRT, mRTld;  // mRT: K1's 128 x 32 store tiles; mRTld: K2's loads
+  float* Ph = RT + (size_t)k.Cpad * n_pad;
+  float* Pl = Ph + (size_t)k.Cpad * p;
+  {
+    const int tot = k.Cpad * p;
+    tc::split_params_kernel<<<(tot + 255) / 256, 256, 0, st>>>(params, C, k.Cpad, plan->P, p, Ph, Pl);
+    LSLB_LAUNCH_CHECK();
+  }
+  if (make_tmap_f32(&mPh, Ph, k.Cpad, p, p, tc::MT, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mPl, Pl, k.Cpad, p, p, tc::MT, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mXh, plan->d_Xh, n, p, p, tc::NR1, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mXl, plan->d_Xl, n, p, p, tc::NR1, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
   const float fis = plan->fam == FAM_NORMAL_FIXED ? (float)(1.0 / plan->desc.fixed_scale) : 1.f;
   const size_t smem1 = tc::STAGES * sizeof(tc::K1Stage) + 2 * 128 * 32 * 4 + 1024;
-  if (make_tmap_f32_k32(&mRT, RT, k.Cpad, n_pad, n_pad, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32_k32(&mRT, RT, (n_pad / 32) * k.Cpad, 32, 32, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
   dim3 grid1(k.ntiles_chain, k.nchunks);
   if (g) {
     auto kern = tc::dense_tc_k1<FAM, true>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 448, smem1, st>>>(mP, mX, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
-                                    k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+    kern<<<grid1, 320, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
+                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   } else {
     auto kern = tc::dense_tc_k1<FAM, false>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 448, smem1, st>>>(mP, mX, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad, p,
-                                    k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+    kern<<<grid1, 320, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
+                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   }
   LSLB_LAUNCH_CHECK();
   if (!g) return LSLB_OK;
-  if (make_tmap_f32_k32(&mXT, plan->d_XT, p, n_pad, n_pad, tc::MT) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mRTld, RT, (n_pad / 32) * k.Cpad, 32, 32, tc::NC2, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mXTh, plan->d_XT, (n_pad / tc::KC) * p, tc::KC, tc::KC, p, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mXTl, plan->d_XTl, (n_pad / tc::KC) * p, tc::KC, tc::KC, p, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
   dim3 grid2(k.ntiles_chain, k.nchunks);
   const int soff = plan->soff[plan->dn[0]];
   if (p == 256) {
-    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<2>) + 1024;
-    auto kern = tc::dense_tc_k2<2>;
+    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<256>) + 1024;
+    auto kern = tc::dense_tc_k2<256>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    kern<<<grid2, 192, smem2, st>>>(mXT, mRT, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall, k.Cpad);
+    kern<<<grid2, 192, smem2, st>>>(mXTh, mXTl, mRTld, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall,
+                                    k.Cpad);
   } else {
-    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<1>) + 1024;
-    auto kern = tc::dense_tc_k2<1>;
+    const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<128>) + 1024;
+    auto kern = tc::dense_tc_k2<128>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    kern<<<grid2, 192, smem2, st>>>(mXT, mRT, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall, k.Cpad);
+    kern<<<grid2, 192, smem2, st>>>(mXTh, mXTl, mRTld, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall,
+                                    k.Cpad);
   }
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;

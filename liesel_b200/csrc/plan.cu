@@ -278,7 +278,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
 extern "C" void lslb_plan_destroy(lslb_plan* p) {
   if (!p) return;
   if (p->d_chunk_start) cudaFree(p->d_chunk_start);
-  if (p->d_XT) cudaFree(p->d_XT);
+  lslb::dense_tc_release(p);
   delete p;
 }
 

@@ -41,13 +41,15 @@ __device__ __forceinline__ void mbar_wait_parity(u64t* bar, unsigned parity) {
 }
 // K-major operand tile, 128-byte swizzle, rows of exactly 128 bytes (32 fp32):
 // SBO = 8 rows * 128 B, LBO unused, version 1 (sm_100), layout SWIZZLE_128B (= 2)
-__device__ __forceinline__ u64t umma_desc_k_sw128(const void* smem, unsigned k_byte_offset) {
+// With rows of 64 bytes (16 fp32) the layout is SWIZZLE_64B (= 4) and SBO = 8 rows * 64 B.
+template <int PKT>
+__device__ __forceinline__ u64t umma_desc_k(const void* smem, unsigned k_byte_offset) {
   const unsigned addr = tsmem(smem) + k_byte_offset;
   u64t d = 0;
   d |= (u64t)((addr >> 4) & 0x3FFF);
-  d |= (u64t)(1024 >> 4) << 32;
+  d |= (u64t)((8 * PKT * 4) >> 4) << 32;
   d |= (u64t)1 << 46;
-  d |= (u64t)2 << 61;
+  d |= (u64t)(PKT == 32 ? 2 : 4) << 61;
   return d;
 }
 // instruction descriptor: D = fp32, A = B = tf32, both K-major, dense
@@ -66,9 +68,7 @@ __device__ __forceinline__ void umma_commit(u64t* bar) {
                : "memory");
 }
 
-constexpr int PK = 32;  // K chunk (floats): one 128-byte swizzle row
-
-template <int N>
+template <int N, int PK>  // PK = K chunk (floats): one swizzle row of 128 (PK = 32) or 64 bytes (PK = 16)
 __global__ void __launch_bounds__(128, 1)
 tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int K,
                 int split, float* __restrict__ D) {
@@ -128,10 +128,10 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
       for (int k8 = 0; k8 < PK / 8; ++k8) {
         const unsigned kb = k8 * 32;  // 8 tf32 = 32 bytes
-        umma_tf32(tmem_d, umma_desc_k_sw128(sA, kb), umma_desc_k_sw128(sB, kb), idesc, (kc | k8) != 0);
+        umma_tf32(tmem_d, umma_desc_k<PK>(sA, kb), umma_desc_k<PK>(sB, kb), idesc, (kc | k8) != 0);
         if (split) {
-          umma_tf32(tmem_d, umma_desc_k_sw128(sAl, kb), umma_desc_k_sw128(sB, kb), idesc, 1);
-          umma_tf32(tmem_d, umma_desc_k_sw128(sA, kb), umma_desc_k_sw128(sBl, kb), idesc, 1);
+          umma_tf32(tmem_d, umma_desc_k<PK>(sAl, kb), umma_desc_k<PK>(sB, kb), idesc, 1);
+          umma_tf32(tmem_d, umma_desc_k<PK>(sA, kb), umma_desc_k<PK>(sBl, kb), idesc, 1);
         }
       }
       umma_commit(&bar_mma);
@@ -170,8 +170,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D fp32 tensor map over a row-major [rows x cols] matrix (row stride ld floats), box = {32 cols, box_rows},
 // 128-byte swizzle
-int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
-                      int box_rows) {
+int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
+                  int box_rows, int kc) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -182,12 +182,18 @@ int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long 
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? LSLB_OK : LSLB_ERR_CUDA;
+}
+
+int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
+                      int box_rows) {
+  return make_tmap_f32(map, base, rows, cols, ld, box_rows, 32);
 }
 
 }  // namespace lslb
@@ -197,16 +203,24 @@ extern "C" int lslb_debug_tc_probe(const float* A, const float* B, int N, int K,
                                    lslb_stream_t stream) {
   using namespace lslb;
   if (!A || !B || !D || K < 32 || (K % 32) != 0) return LSLB_ERR_INVALID;
+  const int PKH = (split & 2) ? 16 : 32;  // bit 1 of `split`: 16-float chunks, 64-byte swizzle
+  split &= 1;
   CUtensorMap mA, mB;
-  if (make_tmap_f32_k32(&mA, A, 128, K, K, 128) != LSLB_OK) return LSLB_ERR_CUDA;
-  if (make_tmap_f32_k32(&mB, B, N, K, K, N) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mA, A, 128, K, K, 128, PKH) != LSLB_OK) return LSLB_ERR_CUDA;
+  if (make_tmap_f32(&mB, B, N, K, K, N, PKH) != LSLB_OK) return LSLB_ERR_CUDA;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = (size_t)2 * (128 + N) * PK * 4 + 1024;
+  const size_t smem = (size_t)2 * (128 + N) * PKH * 4 + 1024;
 #define LSLB_TC_GO(NN)                                                                                  \
   do {                                                                                                  \
-    auto kern = tc_probe_kernel<NN>;                                                                    \
-    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<1, 128, smem, s>>>(mA, mB, K, split, D);                                                     \
+    if (PKH == 32) {                                                                                    \
+      auto kern = tc_probe_kernel<NN, 32>;                                                              \
+      LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+      kern<<<1, 128, smem, s>>>(mA, mB, K, split, D);                                                   \
+    } else {                                                                                            \
+      auto kern = tc_probe_kernel<NN, 16>;                                                              \
+      LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+      kern<<<1, 128, smem, s>>>(mA, mB, K, split, D);                                                   \
+    }                                                                                                   \
   } while (0)
   if (N == 64) LSLB_TC_GO(64);
   else if (N == 128) LSLB_TC_GO(128);
