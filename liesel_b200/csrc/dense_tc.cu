@@ -19,8 +19,8 @@
 // memory by dedicated warps (element-wise, hence blind to the swizzled layout).
 //
 // Warp roles, mbarrier pipelines:
-//   K1 (10 warps): TMA warp --full--> MMA warp --(commit) empty--> TMA warp;
-//                  MMA warp --(commit) tmem_full--> 8 epilogue warps --tmem_empty--> MMA warp (2 accumulators)
+//   K1 (18 warps): TMA warp --full--> MMA warp --(commit) empty--> TMA warp;
+//                  MMA warp --(commit) tmem_full--> 16 epilogue warps --tmem_empty--> MMA warp (2 accumulators)
 //   K2 (6 warps):  TMA warp --full_raw--> 4 split warps --full_split--> MMA warp --(commit) empty--> TMA warp
 #include <cuda.h>
 #include <stdlib.h>
@@ -35,13 +35,19 @@ int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long 
 int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
                   int kc);
 
+#ifndef LSLB_TC_COPY_OUT
+#define LSLB_TC_COPY_OUT 0  // 1: coalesced st.global copy-out of the residual tile instead of a TMA store (same speed)
+#endif
+
 namespace tc {
-constexpr int KC = 32;        // K chunk in floats: one 64-byte swizzle row (48 KB stages, 4 in flight:
+constexpr int KC = 16;        // K chunk in floats: one 64-byte swizzle row (48 KB stages, 4 in flight:
                               // the loads come from DRAM and two 96 KB stages could not cover its latency)
 constexpr int MT = 128;       // M tile (TMEM lanes)
 constexpr int NR1 = 256;      // K1: rows (N) per tile
 constexpr int NC2 = 128;      // K2: chains (N) per CTA
-constexpr int STAGES = 2;
+constexpr int STAGES = 4;    // K2 ring
+constexpr int STAGES1 = 3;   // K1 ring (leaves room for the residual staging tiles)
+constexpr int K1_GROUPS = 4; // K1 epilogue: groups of 4 warps (one per TMEM lane quarter), NR1/K1_GROUPS rows each
 
 __device__ __forceinline__ unsigned sm(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(u64t* b, int c) {
@@ -126,11 +132,12 @@ __device__ __forceinline__ void bar_named(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-struct Pipe {  // (stage, phase) cursor of one role
+template <int NSTAGES>
+struct PipeT {  // (stage, phase) cursor of one role
   int s = 0;
   unsigned ph = 0;
   __device__ __forceinline__ void next() {
-    if (++s == STAGES) { s = 0; ph ^= 1; }
+    if (++s == NSTAGES) { s = 0; ph ^= 1; }
   }
 };
 
@@ -143,7 +150,7 @@ struct K1Stage {
 };
 
 template <int FAM, bool GRAD>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(64 + 128 * K1_GROUPS, 1)
 dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
             const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
             const __grid_constant__ CUtensorMap mapRT, const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
@@ -151,8 +158,9 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
   K1Stage* st = reinterpret_cast<K1Stage*>(smraw);
-  float* stage_out = reinterpret_cast<float*>(smraw + STAGES * sizeof(K1Stage));  // [128 chains][32 rows], SW128
-  __shared__ __align__(8) u64t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  float* stage_out = reinterpret_cast<float*>(smraw + STAGES1 * sizeof(K1Stage));  // [128 chains][32 rows], SW128
+  __shared__ __align__(8) u64t full[STAGES1], empty[STAGES1], tmem_full[2], tmem_empty[2];
+  __shared__ float lp_s[K1_GROUPS][MT];
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chain0 = blockIdx.x * MT;
@@ -161,13 +169,13 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
   const int nk = p / KC;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < STAGES1; ++s) {
       bar_init(&full[s], 1);
       bar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       bar_init(&tmem_full[a], 1);
-      bar_init(&tmem_empty[a], 256);
+      bar_init(&tmem_empty[a], 128 * K1_GROUPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -184,7 +192,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
-      Pipe q;
+      PipeT<STAGES1> q;
       for (int t = 0; t < my_tiles; ++t) {
         const int row0 = (tile0 + t) * NR1;
         for (int kc = 0; kc < nk; ++kc) {
@@ -201,7 +209,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      Pipe q;
+      PipeT<STAGES1> q;
       const unsigned idesc = idesc_tf32(MT, NR1);
       for (int t = 0; t < my_tiles; ++t) {
         const int acc = t & 1;
@@ -227,27 +235,28 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
       }
     }
   } else {
-    // ---------------- epilogue warps (2 x 128 threads): thread = TMEM lane = chain ----------------
-    // two warps per lane quarter; each takes one half (128 of the 256 rows) of every tile. The
-    // likelihood is evaluated branch-free for all 32 rows of a block so that the independent
-    // MUFU/FMA chains interleave (a lone warp per scheduler has only its own ILP to hide latency).
+    // ---------------- epilogue warps (K1_GROUPS x 128 threads): thread = TMEM lane = chain ----------
+    // K1_GROUPS warps per lane quarter; group g takes rows [g, g+1) * NR1/K1_GROUPS of every tile. The
+    // per-row likelihood is a latency-bound chain of MUFU ops: the epilogue of a tile must finish
+    // within the MMA time of the next one (two accumulators), which takes 4 warps per scheduler.
+    constexpr int GR = NR1 / K1_GROUPS;    // rows per group
     const int q4 = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // 0: rows 0..127 of the tile, 1: rows 128..255
-    const int first = 64 + half * 128;     // first thread of this half (issues the TMA stores)
+    const int half = (warp - 2) >> 2;      // group index
+    const int first = 64 + half * 128;     // first thread of this group (issues the TMA stores)
     const int chain = chain0 + q4 * 32 + lane;
     const int rloc = q4 * 32 + lane;       // chain within the tile = row of the staging tile
-    float* sbuf = stage_out + half * (128 * 32);
+    float* sbuf = stage_out + half * (128 * 32);  // one staging tile per group
     float lp_hi = 0.f, lp_lo = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      const long long row0 = (long long)(tile0 + t) * NR1 + half * 128;
+      const long long row0 = (long long)(tile0 + t) * NR1 + half * GR;
       bar_wait(&tmem_full[acc], (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;");
       float lp_tile = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < GR; c0 += 32) {
         unsigned r[32];
-        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(acc * NR1 + half * 128 + c0), r);
+        tmem_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(acc * NR1 + half * GR + c0), r);
         float dres[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -261,9 +270,29 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
         }
         if constexpr (GRAD) {
           // residual tile -> swizzled staging -> one TMA store (full 128-byte lines of R^T per chain)
+          float4* srow = reinterpret_cast<float4*>(sbuf + rloc * 32);
+#if LSLB_TC_COPY_OUT
+          // residual tile -> swizzled staging -> coalesced copy-out with ordinary stores: in the blocked
+          // layout R^T[row/32][chain][32] the tile is 16 KB of CONTIGUOUS global memory.
+          bar_named(1 + half, 128);         // the previous copy-out has finished reading the staging tile
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            srow[j ^ (rloc & 7)] = make_float4(dres[4 * j], dres[4 * j + 1], dres[4 * j + 2], dres[4 * j + 3]);
+          bar_named(1 + half, 128);
+          {
+            float4* gdst = reinterpret_cast<float4*>(RT + ((size_t)((row0 + c0) / 32) * Cpad + chain0) * 32);
+            const float4* ssrc = reinterpret_cast<const float4*>(sbuf);
+            const int tg = tid - first;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int g = i * 128 + tg, row = g >> 3, slot = g & 7;
+              gdst[g] = ssrc[row * 8 + (slot ^ (row & 7))];
+            }
+          }
+#else
+          // residual tile -> swizzled staging -> one TMA store (full 128-byte lines of R^T per chain)
           if (tid == first) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           bar_named(1 + half, 128);         // the previous store has drained the staging buffer
-          float4* srow = reinterpret_cast<float4*>(sbuf + rloc * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             srow[j ^ (rloc & 7)] = make_float4(dres[4 * j], dres[4 * j + 1], dres[4 * j + 2], dres[4 * j + 3]);
@@ -273,6 +302,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
             tma_store2d(&mapRT, sbuf, 0, (int)((row0 + c0) / 32) * Cpad + chain0);  // blocked R^T: [row/32][chain][32]
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+#endif
         }
       }
       kahan_add(lp_hi, lp_lo, lp_tile);
@@ -280,11 +310,18 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
       bar_arrive(&tmem_empty[acc]);
     }
     if (GRAD && tid == first) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    // finalize sums (row Psmall) - (row Psmall+1): half 0 contributes +lp, half 1 contributes -(-lp)
-    float* out = partial + (size_t)blockIdx.y * (Psmall + LSLB_NACC) * Cpad + chain;
-    const float lp = lp_hi - lp_lo;
-    if (half == 0) out[(size_t)Psmall * Cpad] = lp;
-    else out[(size_t)(Psmall + 1) * Cpad] = -lp;
+    // the groups' log-likelihood sums are combined in a fixed order; finalize computes
+    // (row Psmall) - (row Psmall+1)
+    lp_s[half][rloc] = lp_hi - lp_lo;
+    bar_named(1 + K1_GROUPS, 128 * K1_GROUPS);
+    if (half == 0) {
+      float lp = 0.f;
+#pragma unroll
+      for (int g = 0; g < K1_GROUPS; ++g) lp += lp_s[g][rloc];
+      float* out = partial + (size_t)blockIdx.y * (Psmall + LSLB_NACC) * Cpad + chain;
+      out[(size_t)Psmall * Cpad] = lp;
+      out[(size_t)(Psmall + 1) * Cpad] = 0.f;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -338,7 +375,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      Pipe q;
+      PipeT<STAGES> q;
       for (int kc = 0; kc < my_k; ++kc) {
         const int r0 = (k0 + kc) * KC;
         bar_wait(&empty[q.s], q.ph ^ 1);
@@ -351,7 +388,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      Pipe q;
+      PipeT<STAGES> q;
       const unsigned idesc = idesc_tf32(NC2, NP);
       for (int kc = 0; kc < my_k; ++kc) {
         bar_wait(&full_split[q.s], q.ph);
@@ -374,7 +411,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ 
     // split warps (residual tile only), then epilogue: warps 2..5 cover the four TMEM lane
     // quarters (warp & 3 = 2,3,0,1); thread = chain, columns = coefficients
     const int t128 = tid - 64;
-    Pipe q;
+    PipeT<STAGES> q;
     for (int kc = 0; kc < my_k; ++kc) {
       bar_wait(&full_raw[q.s], q.ph);
       split_tile(st[q.s].ah, st[q.s].al, NC2 * KC, t128, 128);
@@ -562,18 +599,18 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
   if (make_tmap_f32(&mXh, plan->d_Xh, n, p, p, tc::NR1, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
   if (make_tmap_f32(&mXl, plan->d_Xl, n, p, p, tc::NR1, tc::KC) != LSLB_OK) return LSLB_ERR_CUDA;
   const float fis = plan->fam == FAM_NORMAL_FIXED ? (float)(1.0 / plan->desc.fixed_scale) : 1.f;
-  const size_t smem1 = tc::STAGES * sizeof(tc::K1Stage) + 2 * 128 * 32 * 4 + 1024;
+  const size_t smem1 = tc::STAGES1 * sizeof(tc::K1Stage) + 4 * 128 * 32 * 4 + 1024;
   if (make_tmap_f32_k32(&mRT, RT, (n_pad / 32) * k.Cpad, 32, 32, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
   dim3 grid1(k.ntiles_chain, k.nchunks);
   if (g) {
     auto kern = tc::dense_tc_k1<FAM, true>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 320, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
+    kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
                                     p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   } else {
     auto kern = tc::dense_tc_k1<FAM, false>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    kern<<<grid1, 320, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
+    kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
                                     p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
   }
   LSLB_LAUNCH_CHECK();
