@@ -370,3 +370,51 @@ class BatchedNUTS:
         self.logp, self.grad = self.f(self.q)
         self.logp, self.grad = self.logp.clone(), self.grad.clone()
         self.evals += 1
+
+
+# =============================================================================================
+# HMC with a fixed number of leapfrog steps (reference: goose/hmc.py)
+# =============================================================================================
+@dataclass
+class HMCInfo:
+    error_code: torch.Tensor      # int32 [C]: 1 = divergent transition (hmc.py:67-77, error_book :131)
+    acceptance_prob: torch.Tensor
+    position_moved: torch.Tensor  # bool [C]
+    divergent: torch.Tensor       # bool [C]
+    num_evals: int
+
+
+class BatchedHMC(BatchedNUTS):
+    """
+    Batched counterpart of the reference's ``HMCKernel`` (``src/liesel/goose/hmc.py``): every
+    transition integrates ``num_integration_steps`` leapfrog steps (default 10, :149) from a fresh
+    momentum and accepts the end point with probability ``min(1, exp(H0 - H1))``; a transition is
+    divergent when ``H1 - H0`` exceeds the threshold 1000 (:62-66; a NaN energy counts as +inf).
+    Dual averaging, the Stan-style warm-up epochs and the mass-matrix tuning are shared with
+    ``BatchedNUTS`` (the reference shares ``da_step`` / ``tune_inv_mm_diag`` between both kernels,
+    hmc.py:255-336). One batched logp+grad call per leapfrog step, all chains in lock-step.
+    """
+
+    def __init__(self, logp_grad_fn: Callable, q0: torch.Tensor, num_integration_steps: int = 10, **kw):
+        kw.setdefault("fused", False)
+        self.num_integration_steps = int(num_integration_steps)
+        super().__init__(logp_grad_fn, q0, **kw)
+
+    @torch.no_grad()
+    def transition(self) -> HMCInfo:
+        evals0 = self.evals
+        r0 = self._randn(self.C, self.P) / self.inv_mass.sqrt()
+        h0 = -self.logp + self._kinetic(r0)
+        q, r, lp, g = self.q, r0, self.logp, self.grad
+        for _ in range(self.num_integration_steps):
+            q, r, lp, g = self._leapfrog(q, r, g, self.step_size)
+        h1 = -lp + self._kinetic(r)
+        delta = torch.nan_to_num(h0 - h1, nan=-float("inf"))  # blackjax safe_energy_diff
+        divergent = -delta > self.div_thr
+        p_accept = torch.exp(torch.clamp(delta, max=0.0))
+        accept = self._rand(self.C) < p_accept
+        sel = accept[:, None]
+        self.q = torch.where(sel, q, self.q)
+        self.grad = torch.where(sel, g, self.grad)
+        self.logp = torch.where(accept, lp, self.logp)
+        return HMCInfo(divergent.to(torch.int32), p_accept, accept, divergent, self.evals - evals0)

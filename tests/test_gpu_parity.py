@@ -611,3 +611,25 @@ def test_device_diagnostics_on_gpu(lb):
     t = torch.as_tensor(x, device="cuda")
     np.testing.assert_allclose(diagnostics.ess_bulk_device(t), diagnostics.ess_bulk(x), rtol=1e-8)
     np.testing.assert_allclose(diagnostics.split_rhat_device(t), diagnostics.split_rhat(x), rtol=1e-8)
+
+
+def test_hmc_on_device(lb):
+    """BatchedHMC (HMCKernel mirror) driven by the CUDA log-prob/gradient: adapts to the target
+    acceptance and leaves rejected chains untouched."""
+    from liesel_b200.nuts import BatchedHMC
+
+    spec, centre = make("s1", np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 64)
+    f = lambda q: plan.logp_grad(q, None)  # noqa: E731
+    s = BatchedHMC(f, dev(th, plan), seed=5, num_integration_steps=8)
+    s.warmup(150, init_duration=40, term_duration=60, base_duration=25)
+    q_before = s.q.clone()
+    info = s.transition()
+    assert info.num_evals == 8
+    kept = ~info.position_moved
+    assert torch.equal(s.q[kept], q_before[kept])
+    draws, infos = s.sample(60)
+    acc = float(torch.stack([i.acceptance_prob for i in infos]).mean())
+    assert 0.6 < acc < 0.97
+    assert torch.isfinite(draws).all()

@@ -116,3 +116,49 @@ def test_device_diagnostics_match_host_versions():
     r = diagnostics.split_rhat(x)
     np.testing.assert_allclose(diagnostics.split_rhat_device(t), r, rtol=1e-9)
     assert r[0] < 1.05 and r[2] > 1.1
+
+
+def test_hmc_recovers_model_lm(golden_dir):
+    """The reference's HMC kernel test (tests/goose/kernels/test_hmc.py via model_lm.py:70-84)."""
+    g = json.load(open(os.path.join(golden_dir, "model_lm.json")))
+    X, y = np.array(g["X"]), np.array(g["y"])
+    spec = ModelSpec(dtype=np.dtype(np.float64))
+    spec.add_response(y, "normal").add_predictor("loc").add_predictor("scale")
+    spec.add_p_smooth(X, 0.0, None, "loc", "beta")
+    spec.add_p_smooth(np.ones((30, 1)), 0.0, None, "scale", "log_sigma")
+    prep = sam.Prepared(spec)
+
+    def f(q):
+        th = q.numpy()
+        return (torch.from_numpy(sam.log_prob(spec, th, prep=prep)),
+                torch.from_numpy(sam.grad(spec, th, prep=prep)))
+
+    q0 = torch.tensor([g["beta"] + [g["log_sigma"]]], dtype=torch.float64).repeat(4, 1)
+    s = nuts.BatchedHMC(f, q0, seed=7)
+    assert s.num_integration_steps == 10  # hmc.py:149
+    s.warmup(5000, term_duration=4000)  # model_lm.py:56-60
+    draws, infos = s.sample(800)
+    d = draws.numpy()
+    assert d[:, :, :2].mean(axis=(0, 1)) == pytest.approx(np.array(g["beta_ols"]), rel=0.05)
+    assert d[:, :, 2].mean() == pytest.approx(np.log(g["sigma_ols"]), rel=0.05)
+    acc = np.mean([float(i.acceptance_prob.mean()) for i in infos])
+    assert acc == pytest.approx(0.8, abs=0.05)
+    assert all(i.num_evals == 10 for i in infos)
+    codes = np.concatenate([i.error_code.numpy() for i in infos])
+    assert (codes == 0).mean() > 0.98
+    moved = np.mean([float(i.position_moved.float().mean()) for i in infos])
+    assert 0.6 < moved < 0.95
+
+
+def test_hmc_nan_energy_is_divergent_and_rejected():
+    def f(q):
+        lp = torch.where(q[:, 0] > 0.5, torch.full_like(q[:, 0], float("nan")), -0.5 * (q * q).sum(dim=1))
+        return lp, -q
+
+    s = nuts.BatchedHMC(f, torch.zeros(8, 2, dtype=torch.float64), seed=3, initial_step_size=5.0,
+                        num_integration_steps=3)
+    q_before = s.q.clone()
+    info = s.transition()
+    bad = info.divergent
+    assert torch.equal(s.q[bad], q_before[bad])
+    assert (info.acceptance_prob[bad] == 0).all() and (info.error_code[bad] == 1).all()
