@@ -398,10 +398,35 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version
+    # banner on stdout under NCCL_DEBUG=VERSION), so everything but the result line goes to stderr:
+    # file descriptor 1 is pointed at stderr for the run and the line is written to the saved one.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    global print
+    builtin_print = print
+
+    def capture(*a, **k):
+        if k.get("file") is None:
+            lines.append(" ".join(str(x) for x in a))
+        else:
+            builtin_print(*a, **k)
+
+    print = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        print = builtin_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        builtin_print(ln, flush=True)
 
 
 if __name__ == "__main__":
