@@ -14,7 +14,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libliesel_b200.so")
+# LSLB_LIB_PATH: A/B measurements of two builds of the same library (tools only)
+LIB_PATH = os.environ.get("LSLB_LIB_PATH") or os.path.join(_HERE, "csrc", "libliesel_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

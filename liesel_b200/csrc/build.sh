@@ -10,7 +10,7 @@ mkdir -p build
 pids=()
 for s in "${SRCS[@]}"; do
   o=build/${s%.cu}.o
-  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || prologue.cuh -nt $o || x2_common.cuh -nt $o || ../../include/liesel_b200.h -nt $o ]]; then
+  if [[ ! -f $o || $s -nt $o || common.cuh -nt $o || prologue.cuh -nt $o || x2_common.cuh -nt $o || tc_bf16.cuh -nt $o || ../../include/liesel_b200.h -nt $o ]]; then
     ( $NVCC "${FLAGS[@]}" -c "$s" -o "$o" > "build/${s%.cu}.log" 2>&1 || { cat "build/${s%.cu}.log"; exit 1; } ) &
     pids+=($!)
   fi

@@ -10,6 +10,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_bf16.cuh"
 
 namespace lslb {
 
@@ -164,6 +165,93 @@ tc_probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mixed-precision 3-pass product: hi(A).hi(B) in TF32 plus the two CORRECTION passes in BF16
+//   bf16(lo(A)).bf16(B) + bf16(A).bf16(lo(B))       (kind::f16, twice the rate of kind::tf32)
+// accumulated into the same fp32 TMEM accumulator. The corrections are 2^-11 of the result, so
+// BF16's 2^-9 relative rounding leaves 2^-19..2^-20 per product. K chunks of 16 floats: fp32 tiles
+// have 64-byte rows (SWIZZLE_64B), bf16 tiles 32-byte rows (SWIZZLE_32B). The bf16 tiles are
+// produced in shared memory from the fp32 tile at explicit swizzled addresses (this is the code
+// the K2 kernel of dense_tc.cu uses for the residual tile; helpers in tc_bf16.cuh).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128, 1)
+tc_probe_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int K,
+                     float* __restrict__ D) {
+  constexpr int PK = 16;
+  extern __shared__ unsigned char smraw_[];
+  unsigned char* smraw = smraw_ + ((1024u - (tsmem(smraw_) & 1023u)) & 1023u);
+  float* sA = reinterpret_cast<float*>(smraw);                    // [128][16] fp32, SW64
+  float* sB = sA + 128 * PK;                                      // [N][16]
+  unsigned char* sAb = reinterpret_cast<unsigned char*>(sB + N * PK);  // [128][16] bf16, SW32
+  unsigned char* sAlb = sAb + 128 * 32;
+  unsigned char* sBb = sAlb + 128 * 32;
+  unsigned char* sBlb = sBb + N * 32;
+  __shared__ __align__(8) u64t bar_tma, bar_mma;
+  __shared__ unsigned tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init1(&bar_tma, 1);
+    mbar_init1(&bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tsmem(&tmem_base)),
+                 "r"(N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const unsigned tmem_d = tmem_base;
+  const unsigned idesc = umma_idesc_tf32(128, N), idesc16 = tcx::idesc_bf16(128, N);
+  for (int kc = 0; kc < K / PK; ++kc) {
+    if (tid == 0) {
+      mbar_expect(&bar_tma, (128 + N) * PK * 4);
+      tma_load_2d(sA, &mapA, kc * PK, 0, &bar_tma);
+      tma_load_2d(sB, &mapB, kc * PK, 0, &bar_tma);
+    }
+    mbar_wait_parity(&bar_tma, kc & 1);
+    tcx::split_tile_bf16(sA, sAb, sAlb, 128, tid, 128);
+    tcx::split_tile_bf16(sB, sBb, sBlb, N, tid, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int k8 = 0; k8 < PK / 8; ++k8)
+        umma_tf32(tmem_d, umma_desc_k<PK>(sA, k8 * 32), umma_desc_k<PK>(sB, k8 * 32), idesc, (kc | k8) != 0);
+      tcx::mma_bf16(tmem_d, tcx::desc_k_sw32(sAlb), tcx::desc_k_sw32(sBb), idesc16, 1);
+      tcx::mma_bf16(tmem_d, tcx::desc_k_sw32(sAb), tcx::desc_k_sw32(sBlb), idesc16, 1);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait_parity(&bar_mma, kc & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;");
+  }
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    unsigned r[32];
+    const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(N));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -191,6 +279,28 @@ int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long
   return r == CUDA_SUCCESS ? LSLB_OK : LSLB_ERR_CUDA;
 }
 
+// 2-D bf16 tensor map over a row-major [rows x cols] matrix (row stride ld elements), box = {16 cols, box_rows},
+// 32-byte swizzle
+int make_tmap_bf16_k16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                       int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return LSLB_ERR_CUDA;
+    fn = (EncodeTiledFn)p;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {16, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LSLB_OK : LSLB_ERR_CUDA;
+}
+
 int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
                       int box_rows) {
   return make_tmap_f32(map, base, rows, cols, ld, box_rows, 32);
@@ -203,7 +313,8 @@ extern "C" int lslb_debug_tc_probe(const float* A, const float* B, int N, int K,
                                    lslb_stream_t stream) {
   using namespace lslb;
   if (!A || !B || !D || K < 32 || (K % 32) != 0) return LSLB_ERR_INVALID;
-  const int PKH = (split & 2) ? 16 : 32;  // bit 1 of `split`: 16-float chunks, 64-byte swizzle
+  const int PKH = (split & 6) ? 16 : 32;  // bit 1 of `split`: 16-float chunks, 64-byte swizzle
+  const bool bf16corr = (split & 4) != 0;  // bit 2: TF32 main pass + two BF16 correction passes
   split &= 1;
   CUtensorMap mA, mB;
   if (make_tmap_f32(&mA, A, 128, K, K, 128, PKH) != LSLB_OK) return LSLB_ERR_CUDA;
@@ -222,6 +333,22 @@ extern "C" int lslb_debug_tc_probe(const float* A, const float* B, int N, int K,
       kern<<<1, 128, smem, s>>>(mA, mB, K, split, D);                                                   \
     }                                                                                                   \
   } while (0)
+  if (bf16corr) {
+    const size_t smem16 = (size_t)(128 + N) * 16 * 4 + (size_t)2 * (128 + N) * 32 + 1024;
+#define LSLB_TC_GO16(NN)                                                                                \
+  do {                                                                                                  \
+    auto kern = tc_probe_bf16_kernel<NN>;                                                               \
+    LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));   \
+    kern<<<1, 128, smem16, s>>>(mA, mB, K, D);                                                          \
+  } while (0)
+    if (N == 64) LSLB_TC_GO16(64);
+    else if (N == 128) LSLB_TC_GO16(128);
+    else if (N == 256) LSLB_TC_GO16(256);
+    else return LSLB_ERR_INVALID;
+#undef LSLB_TC_GO16
+    LSLB_LAUNCH_CHECK();
+    return LSLB_OK;
+  }
   if (N == 64) LSLB_TC_GO(64);
   else if (N == 128) LSLB_TC_GO(128);
   else if (N == 256) LSLB_TC_GO(256);

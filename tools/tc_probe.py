@@ -12,7 +12,7 @@ for N, K in [(128, 32), (128, 64), (64, 256), (256, 256)]:
     A = torch.randn(128, K, device="cuda")
     B = torch.randn(N, K, device="cuda")
     ref = (A.double() @ B.double().T)
-    for split in (0, 1, 2, 3):  # bit 0: 3-pass hi/lo split; bit 1: 16-float chunks (64-byte swizzle)
+    for split in (0, 1, 2, 3, 4):  # bit 0: 3-pass hi/lo split; bit 1: 16-float chunks (64-byte swizzle)
         D = torch.zeros(128, N, device="cuda")
         st = _lib.lib.lslb_debug_tc_probe(_lib.ptr(A), _lib.ptr(B), N, K, split, _lib.ptr(D), _lib.stream_ptr())
         torch.cuda.synchronize()
