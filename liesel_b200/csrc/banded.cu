@@ -70,8 +70,8 @@ struct BandStage {
   int start[NS][BR];
 };
 
-// FAM is FAM_NORMAL_LS or FAM_NORMAL_FIXED (the banded configs of BASELINE.json: S2, S3, H); other
-// families use lik_row.
+// Normal location-scale gets a hand-scheduled form (the banded configs of BASELINE.json: S3, H); the
+// other families use lik_row.
 template <typename T, int FAM>
 __device__ __forceinline__ void lik_fast(T y, T eta0, T eta1, T fixed_inv_scale, T& ll, T& d0, T& d1) {
   if constexpr (FAM == FAM_NORMAL_LS) {
@@ -292,7 +292,6 @@ banded_kernel(const __grid_constant__ EvalParams<T> p, int tiles_per_cta, int nt
 // host ------------------------------------------------------------------------------------------
 bool banded_fast_eligible(const lslb_plan* plan) {
   if (plan->variant != VAR_BANDED || !plan->rows_sorted) return false;
-  if (plan->fam != FAM_NORMAL_LS && plan->fam != FAM_NORMAL_FIXED) return false;
   if (plan->ns > 2) return false;
   auto aligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!aligned(plan->desc.y)) return false;
@@ -345,6 +344,14 @@ int launch_banded(const lslb_plan* plan, const EvalParams<T>& ep, const BandedCf
   if (plan->fam == FAM_NORMAL_LS) {
     if (plan->ns == 1) return banded_launch<T, FAM_NORMAL_LS, 1>(ep, k, g, st);
     return banded_launch<T, FAM_NORMAL_LS, 2>(ep, k, g, st);
+  }
+  if (plan->fam == FAM_POISSON) {
+    if (plan->ns == 1) return banded_launch<T, FAM_POISSON, 1>(ep, k, g, st);
+    return banded_launch<T, FAM_POISSON, 2>(ep, k, g, st);
+  }
+  if (plan->fam == FAM_BERNOULLI) {
+    if (plan->ns == 1) return banded_launch<T, FAM_BERNOULLI, 1>(ep, k, g, st);
+    return banded_launch<T, FAM_BERNOULLI, 2>(ep, k, g, st);
   }
   if (plan->ns == 1) return banded_launch<T, FAM_NORMAL_FIXED, 1>(ep, k, g, st);
   return banded_launch<T, FAM_NORMAL_FIXED, 2>(ep, k, g, st);

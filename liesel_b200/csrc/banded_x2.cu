@@ -102,6 +102,8 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   // Normal location-scale: predictor 1 is carried as -log2(e) * eta1 (its coefficients are scaled
   // once when a run starts), so exp(-eta1) is a bare ex2 with no per-row multiply
   if constexpr (FAM == FAM_NORMAL_LS) o1 = mul2(o1, pk(-1.4426950408889634f, -1.4426950408889634f));
+  // Poisson: predictor 0 is carried as log2(e) * eta0, so the mean exp(eta0) is a bare ex2
+  if constexpr (FAM == FAM_POISSON) o0 = mul2(o0, pk(1.4426950408889634f, 1.4426950408889634f));
   if constexpr (GRAD) {
     for (int j = 0; j < p.Psmall; ++j) *at2(j) = pk(0.f, 0.f);
   }
@@ -115,6 +117,8 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   }
   const u64 NEG1 = pk(-1.f, -1.f);
   const u64 NLOG2E = pk(-1.4426950408889634f, -1.4426950408889634f);
+  const u64 ONE = pk(1.f, 1.f);
+  (void)ONE;
   const u64 INVS_FIXED = pk(p.fixed_inv_scale, p.fixed_inv_scale);
   float lpa_hi = 0.f, lpa_lo = 0.f, lpb_hi = 0.f, lpb_lo = 0.f;  // Kahan pairs, chains a and b
   u64 sr0 = pk(0.f, 0.f), sr1 = pk(0.f, 0.f);
@@ -153,6 +157,10 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 #pragma unroll
         for (int t = 0; t < 4; ++t) wb[m][t] = mul2(wb[m][t], NLOG2E);
       }
+    }
+    if constexpr (FAM == FAM_POISSON) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) wb[m][t] = mul2(wb[m][t], mul2(NLOG2E, NEG1));
     }
     if (fast) {
       const u64 nb1 = mul2(wb[m][1], NEG1);
@@ -203,7 +211,9 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       uni = uni && __all_sync(0xffffffffu, eq);
     }
 
-    u64 sz2 = pk(0.f, 0.f), se1 = pk(0.f, 0.f);  // per-tile sums: z^2 and eta1
+    u64 sz2 = pk(0.f, 0.f), se1 = pk(0.f, 0.f);  // per-tile sums: z^2 and eta1 (Normal); see the other families
+    u64 sl2 = pk(0.f, 0.f);
+    (void)sl2;
 
     // NR rows whose weights/responses are already in registers: forward with wb fixed across rows
     // (u-major), likelihood, backward with the residual fixed across the four weights of a row
@@ -228,6 +238,40 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       u64 d0[NR], d1[NR];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
+        if constexpr (FAM == FAM_POISSON) {
+          // eta0 holds log2(e) * eta: mu = ex2(.), ll = y eta - mu (sz2 = sum y eta', se1 = sum mu)
+          float ta, tb;
+          upk(eta0[i], ta, tb);
+          const u64 mu = pk(ex2f(ta), ex2f(tb));
+          const u64 yy = bc(yv[i]);
+          sz2 = fma2(yy, eta0[i], sz2);
+          se1 = add2(se1, mu);
+          if constexpr (GRAD) {
+            d0[i] = fma2(mu, NEG1, yy);
+            sr0 = add2(sr0, d0[i]);
+            d1[i] = d0[i];
+          }
+        } else if constexpr (FAM == FAM_BERNOULLI) {
+          // a = |eta|, e = exp(-a), s = 1 + e:  pi - 1/2 = copysign(1/s - 1/2, eta),
+          // ll = (y - 1/2) eta - a/2 - log(s)   (sz2 = sum (y - 1/2) eta, se1 = sum a, sl2 = sum log2 s)
+          const u64 a = eta0[i] & 0x7FFFFFFF7FFFFFFFull;
+          float ta, tb;
+          upk(mul2(a, NLOG2E), ta, tb);
+          const u64 s1 = add2(pk(ex2f(ta), ex2f(tb)), ONE);
+          float sa, sb;
+          upk(s1, sa, sb);
+          const u64 h = add2(pk(rcpf(sa), rcpf(sb)), pk(-0.5f, -0.5f));
+          sl2 = add2(sl2, pk(lg2f(sa), lg2f(sb)));
+          const u64 ym = bc(yv[i] - 0.5f);
+          sz2 = fma2(ym, eta0[i], sz2);
+          se1 = add2(se1, a);
+          if constexpr (GRAD) {
+            const u64 hs = h ^ (eta0[i] & 0x8000000080000000ull);
+            d0[i] = fma2(hs, NEG1, ym);  // y - pi
+            sr0 = add2(sr0, d0[i]);
+            d1[i] = d0[i];
+          }
+        } else {
         const u64 d = fma2(eta0[i], NEG1, bc(yv[i]));  // y - eta0
         u64 inv_s;
         if constexpr (FAM == FAM_NORMAL_LS) {
@@ -246,6 +290,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           d1[i] = d0[i];
           if constexpr (PM != 0) d1[i] = fma2(z, z, NEG1);
         }
+      }  // Normal families
       }
       if constexpr (GRAD) {
 #pragma unroll
@@ -361,8 +406,18 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       e1a *= -0.6931471805599453f;
       e1b *= -0.6931471805599453f;
     }
-    kahan_add(lpa_hi, lpa_lo, fmaf(-0.5f, z2a, -e1a));
-    kahan_add(lpb_hi, lpb_lo, fmaf(-0.5f, z2b, -e1b));
+    if constexpr (FAM == FAM_POISSON) {  // ln2 * sum(y eta') - sum mu
+      kahan_add(lpa_hi, lpa_lo, fmaf(0.6931471805599453f, z2a, -e1a));
+      kahan_add(lpb_hi, lpb_lo, fmaf(0.6931471805599453f, z2b, -e1b));
+    } else if constexpr (FAM == FAM_BERNOULLI) {  // sum (y - 1/2) eta - sum a / 2 - ln2 * sum log2 s
+      float l2a, l2b;
+      upk(sl2, l2a, l2b);
+      kahan_add(lpa_hi, lpa_lo, fmaf(-0.6931471805599453f, l2a, fmaf(-0.5f, e1a, z2a)));
+      kahan_add(lpb_hi, lpb_lo, fmaf(-0.6931471805599453f, l2b, fmaf(-0.5f, e1b, z2b)));
+    } else {
+      kahan_add(lpa_hi, lpa_lo, fmaf(-0.5f, z2a, -e1a));
+      kahan_add(lpb_hi, lpb_lo, fmaf(-0.5f, z2b, -e1b));
+    }
     if constexpr (GRAD && FAM == FAM_NORMAL_LS) {
       const float nr = -(float)rows;
       sr1 = add2(sr1, add2(sz2, pk(nr, nr)));  // sum (z^2 - 1)
@@ -407,6 +462,14 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
       case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st, plan->unit_rows);
       default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st, plan->unit_rows);
     }
+  }
+  if (plan->fam == FAM_POISSON) {
+    if (plan->ns == 1) return x2_launch<FAM_POISSON, 1, 0>(ep, k, g, st, plan->unit_rows);
+    return x2_launch<FAM_POISSON, 2, 0>(ep, k, g, st, plan->unit_rows);
+  }
+  if (plan->fam == FAM_BERNOULLI) {
+    if (plan->ns == 1) return x2_launch<FAM_BERNOULLI, 1, 0>(ep, k, g, st, plan->unit_rows);
+    return x2_launch<FAM_BERNOULLI, 2, 0>(ep, k, g, st, plan->unit_rows);
   }
   if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st, plan->unit_rows);
   return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st, plan->unit_rows);

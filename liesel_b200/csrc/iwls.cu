@@ -521,7 +521,9 @@ BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C);
 
 // packed TMA run-length IWLS kernel: float32 banded Gaussian plans, spline or intercept target
 static bool iwls_fast(const lslb_plan* plan, int tkind) {
+  // the packed IWLS kernel implements the Normal families only; others take the generic kernel
   return plan->desc.dtype == LSLB_F32 && banded_fast_eligible(plan) &&
+         (plan->fam == FAM_NORMAL_LS || plan->fam == FAM_NORMAL_FIXED) &&
          (tkind == TK_SPLINE || tkind == TK_INTERCEPT);
 }
 

@@ -29,13 +29,6 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
-// same instruction, but `volatile`: the compiler keeps volatile asm statements in program order, which
-// lets the caller dictate an issue order that repeats one operand in consecutive instructions
-__device__ __forceinline__ u64 fma2_ordered(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
   u64 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -49,6 +42,17 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
 __device__ __forceinline__ float ex2f(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float rcpf(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2f(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 

@@ -90,6 +90,35 @@ def s3_gamlss(n: int = 1_000_000, k: int = 20, dtype=np.float32, seed: int = 103
     return spec, centre
 
 
+def spline_glm(family: str, n: int = 50_000, k: int = 20, n_smooth: int = 2, dtype=np.float32,
+               seed: int = 106):
+    """
+    Poisson ("poisson") or Bernoulli ("bernoulli") response with an intercept and ``n_smooth`` cubic
+    P-splines of one covariate each in the single predictor (north star: banded P-splines under all
+    three response families). Rows can be span-sorted, so the TMA run-length kernels apply.
+    """
+    rng = np.random.default_rng(seed)
+    spec = ModelSpec(dtype=np.dtype(dtype))
+    xs = rng.uniform(size=(n_smooth, n))
+    eta = 0.3 + sum(0.8 * np.sin(2 * np.pi * xs[j] * (j + 1)) for j in range(n_smooth))
+    if family == "poisson":
+        y = rng.poisson(np.exp(eta)).astype(np.float64)
+        pred = "log_rate"
+    else:
+        y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+        pred = "logits"
+    spec.add_response(y, family).add_predictor(pred)
+    K = pspline_penalty(k, 2)
+    spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, pred, f"{pred}_p0")
+    centre = [[0.3]]
+    for j in range(n_smooth):
+        xj = xs[j].astype(dtype)
+        knots = equidistant_knots(xj, k, 3)
+        spec.add_spline_smooth(xj, knots, K, 1.0, 0.005, pred, f"{pred}_np{j}", tau2_init=1.0)
+        centre.append(0.8 * np.sin(2 * np.pi * _greville(knots.astype(np.float64)) * (j + 1)))
+    return spec, np.concatenate(centre)
+
+
 def s4_logistic(n: int = 10_000_000, p: int = 256, dtype=np.float32, seed: int = 104,
                 rank: int = 0, world_size: int = 1):
     """

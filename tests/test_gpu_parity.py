@@ -104,6 +104,21 @@ def test_centred_splines(lb, C, dtype):
         check_iwls(spec, plan, name, th, aux, chains=[0, 1, 2, C // 2, C - 1])
 
 
+@pytest.mark.parametrize("family", ["poisson", "bernoulli"])
+@pytest.mark.parametrize("n_smooth", [1, 2])
+@pytest.mark.parametrize("C,dtype", [(20, np.float32), (20, np.float64), (300, np.float32)])
+def test_spline_glm_families(lb, family, n_smooth, C, dtype):
+    """P-splines under the Poisson and Bernoulli families: scalar TMA run-length kernel (few chains,
+    fp64) and the packed kernel (fp32, more than 128 chains), log-prob, gradient and IWLS."""
+    spec, centre = synth.spline_glm(family, n=30_000, n_smooth=n_smooth, dtype=dtype)
+    plan = lb.Plan(spec)
+    assert plan.variant.startswith("banded")
+    th, aux = synth.evaluation_points(spec, centre, C, tau2="loguniform")
+    check_logp_grad(spec, plan, th, aux, chains=None if C < 100 else [0, 1, 128, 129, 255, 256, 299])
+    pred = "log_rate" if family == "poisson" else "logits"
+    check_iwls(spec, plan, f"{pred}_np0", th, aux, chains=[0, 1, C - 1])
+
+
 @pytest.mark.parametrize("tau2", ["start", "loguniform"])
 def test_logp_grad_tau2_range(lb, tau2):
     """tau2 spans 1e-3..1e4 during Gibbs sampling; also the reference's start state beta = 0."""
