@@ -282,10 +282,9 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 // order through shared memory, so the result does not depend on scheduling.
 // FIN_G is 8 for wide launches and 32 when the grid would otherwise leave most SMs idle (few chains).
 template <typename T, int FIN_G>
-__global__ void __launch_bounds__(32 * FIN_G)
-finalize_grad_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
-                     const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
-                     T* __restrict__ vsum) {
+__device__ __forceinline__ void finalize_grad_body(const FinalizeParams& fp, const T* __restrict__ partial,
+                                                   const T* __restrict__ pT, const T* __restrict__ aux,
+                                                   T* __restrict__ grad, T* __restrict__ vsum) {
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y;
@@ -341,14 +340,15 @@ __global__ void center_fix_kernel(const __grid_constant__ FinalizeParams fp,
 }
 
 template <typename T, int FIN_G>
-__global__ void __launch_bounds__(32 * FIN_G)
-finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
-                     const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
-                     int gtiles, int G, T* __restrict__ logp) {
+__device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, const T* __restrict__ partial,
+                                                   const T* __restrict__ pT, const T* __restrict__ aux,
+                                                   const T* __restrict__ gpl, int gtiles, int G,
+                                                   T* __restrict__ logp) {
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;  // < Cpad (Cpad is a multiple of 32)
   const int g = threadIdx.y;
   const bool with_prior = !(fp.flags & LSLB_SKIP_PRIOR);
+  (void)G;
   const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
   const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
   const T* lo = hi + fp.Cpad;
@@ -410,6 +410,25 @@ finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restr
     }
   }
   logp[c] = (T)acc;
+}
+
+// value only: one slice of blocks; value + gradient: grid.y = Psmall + 1, the last slice computes the
+// log-posterior while the others reduce the gradient rows (one launch, both run concurrently)
+template <typename T, int FIN_G>
+__global__ void __launch_bounds__(32 * FIN_G)
+finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
+                     const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
+                     int gtiles, int G, T* __restrict__ logp) {
+  finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, logp);
+}
+template <typename T, int FIN_G>
+__global__ void __launch_bounds__(32 * FIN_G)
+finalize_all_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
+                    const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
+                    T* __restrict__ vsum, const T* __restrict__ gpl, int gtiles, int G,
+                    T* __restrict__ logp) {
+  if ((int)blockIdx.y < fp.Psmall) finalize_grad_body<T, FIN_G>(fp, partial, pT, aux, grad, vsum);
+  else finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, logp);
 }
 
 // =======================================================================================
@@ -708,18 +727,17 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   if (st != LSLB_OK) return st;
 
   if (g) {
-    long long total = (long long)plan->Psmall * k.Cpad;
-    if (total > 0) {
-      dim3 fgrid(k.Cpad / 32, plan->Psmall);
-      if ((long long)fgrid.x * fgrid.y < 4LL * plan->sm_count)
-        finalize_grad_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum);
-      else
-        finalize_grad_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum);
-      LSLB_LAUNCH_CHECK();
-      if (plan->Psmall > plan->Preal) {
-        dim3 cgrid((C + 127) / 128, plan->desc.nblocks);
-        center_fix_kernel<T><<<cgrid, 128, 0, stream>>>(fp, L.vsum, grad);
-      }
+    dim3 fgrid(k.Cpad / 32, plan->Psmall + 1);
+    if ((long long)fgrid.x * fgrid.y < 4LL * plan->sm_count)
+      finalize_all_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum,
+                                                                     L.gpl, L.gtiles, G, logp);
+    else
+      finalize_all_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum,
+                                                                   L.gpl, L.gtiles, G, logp);
+    LSLB_LAUNCH_CHECK();
+    if (plan->Psmall > plan->Preal) {
+      dim3 cgrid((C + 127) / 128, plan->desc.nblocks);
+      center_fix_kernel<T><<<cgrid, 128, 0, stream>>>(fp, L.vsum, grad);
       LSLB_LAUNCH_CHECK();
     }
     if (plan->grp >= 0) {
@@ -728,10 +746,11 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
                                                           C, k.Cpad, grad);
       LSLB_LAUNCH_CHECK();
     }
+  } else {
+    finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
+                                                                          L.gpl, L.gtiles, G, logp);
+    LSLB_LAUNCH_CHECK();
   }
-  finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
-                                                                        L.gpl, L.gtiles, G, logp);
-  LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }
 

@@ -57,6 +57,17 @@ def launches(src, dst):
         f.write("| kernel | launches | mean us | share of captured time |\n|---|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / tot:.3f} |\n")
+        # the kernels of ONE evaluation step: this library's kernels that launch as often as the
+        # dominant row-streaming kernel (micro-benchmarks, plan set-up and torch kernels excluded)
+        mine = {k: v for k, v in agg.items() if "lslb::" in k and "peak_kernel" not in k and "probe" not in k}
+        if mine:
+            top = max(mine.items(), key=lambda kv: sum(kv[1]))
+            step = {k: v for k, v in mine.items() if len(v) == len(top[1])}
+            st = sum(sum(v) / len(v) for v in step.values())
+            f.write("\n## One evaluation step (kernels launched once per step)\n\n")
+            f.write("| kernel | mean us | share of the step |\n|---|---:|---:|\n")
+            for k, v in sorted(step.items(), key=lambda kv: -sum(kv[1])):
+                f.write(f"| `{k[:90]}` | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / len(v) / st:.3f} |\n")
     print("wrote", dst)
 
 
