@@ -29,7 +29,13 @@ namespace lslb {
 // Then, over a run of equal spans, eta = b1 + sum_{u != 1} w_u (b_u - b1) and the gradient of b1 is
 // (sum of residuals) - g0 - g2 - g3: three FMAs per smooth and direction instead of four.
 template <int FAM, int NS, int PM, bool GRAD, bool UNITY>
-__global__ void __launch_bounds__(128, 4)
+#ifndef LSLB_X2_NRB
+#define LSLB_X2_NRB 4   // rows per register block (4 or 2)
+#endif
+#ifndef LSLB_X2_MINB
+#define LSLB_X2_MINB 4  // resident CTAs per SM the register budget is set for
+#endif
+__global__ void __launch_bounds__(128, LSLB_X2_MINB)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
   __shared__ __align__(128) XRaw<NS> raw[XSTAGES];
   __shared__ __align__(8) u64 full[XSTAGES];
@@ -321,12 +327,16 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       if constexpr (NR == 4) {
         const float4 v = *reinterpret_cast<const float4*>(&D.y[r]);
         yv[0] = v.x; yv[1] = v.y; yv[2] = v.z; yv[3] = v.w;
+      } else if constexpr (NR == 2) {
+        const float2 v = *reinterpret_cast<const float2*>(&D.y[r]);
+        yv[0] = v.x; yv[1] = v.y;
       } else {
         yv[0] = D.y[r];
       }
     };
     using N1 = std::integral_constant<int, 1>;
-    using N4 = std::integral_constant<int, 4>;
+    using N4 = std::integral_constant<int, LSLB_X2_NRB>;
+    constexpr int NRB = LSLB_X2_NRB;
 
     const bool want_fast = UNITY && uni && rows == XR;
     if (want_fast != fastmode) {  // the accumulators change form: write them out in the old form
@@ -364,18 +374,18 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
         load_block(wa, ya, 0, N4{});
         if (fastmode) {
 #pragma unroll 1
-          for (int r = 0; r < XR; r += 8) {
-            load_block(wbuf, yb, r + 4, N4{});
+          for (int r = 0; r < XR; r += 2 * NRB) {
+            load_block(wbuf, yb, r + NRB, N4{});
             compute_block(wa, ya, N4{}, TFast{});
-            if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
+            if (r + 2 * NRB < XR) load_block(wa, ya, r + 2 * NRB, N4{});
             compute_block(wbuf, yb, N4{}, TFast{});
           }
         } else {
 #pragma unroll 1
-          for (int r = 0; r < XR; r += 8) {
-            load_block(wbuf, yb, r + 4, N4{});
+          for (int r = 0; r < XR; r += 2 * NRB) {
+            load_block(wbuf, yb, r + NRB, N4{});
             compute_block(wa, ya, N4{}, TFull{});
-            if (r + 8 < XR) load_block(wa, ya, r + 8, N4{});
+            if (r + 2 * NRB < XR) load_block(wa, ya, r + 2 * NRB, N4{});
             compute_block(wbuf, yb, N4{}, TFull{});
           }
         }
