@@ -80,15 +80,22 @@ class BatchedNUTS:
                  da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
                  da_t0: int = 10, divergence_threshold: float = 1000.0, seed: int = 0,
                  initial_step_size: float | None = None, fused: bool | None = None,
-                 logp_grad_into: Callable | None = None):
+                 logp_grad_into: Callable | None = None, graphs: bool = False):
         """
         ``fused`` (default: on for CUDA tensors): run the per-leaf bookkeeping in the two CUDA kernels
         ``lslb_nuts_leaf_pre/post`` instead of ~30 torch ops. ``logp_grad_into(q, logp_out, grad_out)``
         optionally evaluates into preallocated buffers (``Plan.logp_grad(..., out=...)``).
+        ``graphs`` (needs ``fused`` and ``logp_grad_into``): the leaves of a subtree are replayed from
+        CUDA graphs, one graph per leaf range [2^(k-1), 2^k) (the ranges between two host-side "is any
+        chain still active" checks), captured on first use; every leaf is five kernel launches, so
+        at small n the launch latency, not the kernels, bounds a transition.
         """
         self.f = logp_grad_fn
         self.f_into = logp_grad_into
         self.fused = bool(q0.is_cuda) if fused is None else bool(fused)
+        self.use_graphs = bool(graphs) and self.fused and logp_grad_into is not None
+        self._graphs: dict = {}
+        self._graph_ready = False
         self.q = q0.clone()
         self.C, self.P = q0.shape
         self.dev, self.dt = q0.device, q0.dtype
@@ -184,9 +191,14 @@ class BatchedNUTS:
         if st is None:
             z2 = lambda: torch.empty((C, P), dtype=dt, device=dev)
             z1 = lambda: torch.empty(C, dtype=dt, device=dev)
-            st = {k: z2() for k in ("q_e", "r_e", "g_e", "q_n", "r_half", "g_n", "q_s", "g_s", "rsum_s")}
+            st = {k: z2() for k in ("q_e", "r_e", "g_e", "q_n", "r_half", "g_n", "q_s", "g_s", "rsum_s", "inv_mass")}
             st.update({k: z1() for k in ("lp_n", "lp_s", "logw_s", "sum_acc", "n_leaf", "eps", "h0")})
             st.update({k: torch.empty(C, dtype=torch.uint8, device=dev) for k in ("act", "turn_s", "div_s")})
+            # persistent copies of what the caller allocates per transition / per subtree, so that
+            # captured graphs keep pointing at live memory
+            st["U"] = torch.empty((2 ** max(self.max_treedepth - 1, 0), C), dtype=dt, device=dev)
+            st["ck_r"] = torch.empty((C, self.max_treedepth + 1, P), dtype=dt, device=dev)
+            st["ck_s"] = torch.empty_like(st["ck_r"])
             self._fused_state = st
         st["q_e"].copy_(q_e); st["r_e"].copy_(r_e); st["g_e"].copy_(g_e)
         st["q_s"].copy_(q_e); st["g_s"].copy_(g_e); st["lp_s"].copy_(lp_prop)
@@ -194,32 +206,55 @@ class BatchedNUTS:
         st["sum_acc"].zero_(); st["n_leaf"].zero_()
         st["eps"].copy_(eps); st["h0"].copy_(h0)
         st["act"].copy_(alive.to(torch.uint8)); st["turn_s"].zero_(); st["div_s"].zero_()
-        inv_mass = self.inv_mass.contiguous()
+        st["inv_mass"].copy_(self.inv_mass)
+        n_leaves = 2 ** j
+        st["U"][:n_leaves].copy_(U)
+        st["ck_r"].copy_(ck_r); st["ck_s"].copy_(ck_s)
         sfx = _lib.sfx(dt)
         pre = getattr(_lib.lib, "lslb_nuts_leaf_pre_" + sfx)
         post = getattr(_lib.lib, "lslb_nuts_leaf_post_" + sfx)
         order = ["q_e", "r_e", "g_e", "q_n", "r_half", "g_n", "lp_n"]
-        tens = [st[k] for k in order] + [st["eps"], inv_mass, st["h0"], st["q_s"], st["g_s"], st["lp_s"],
-                                         st["logw_s"], st["rsum_s"], ck_r, ck_s, st["sum_acc"], st["n_leaf"],
-                                         st["act"], st["turn_s"], st["div_s"], U]
+        tens = [st[k] for k in order] + [st["eps"], st["inv_mass"], st["h0"], st["q_s"], st["g_s"], st["lp_s"],
+                                         st["logw_s"], st["rsum_s"], st["ck_r"], st["ck_s"], st["sum_acc"],
+                                         st["n_leaf"], st["act"], st["turn_s"], st["div_s"], st["U"]]
         ptrs = (Ct.c_void_p * 23)(*[t.data_ptr() for t in tens])
-        ints = (Ct.c_int * 6)(C, P, ck_r.shape[1], 0, 0, 0)
-        stream = _lib.stream_ptr()
-        n_leaves = 2 ** j
-        for i in range(n_leaves):
-            if i in (1, 3, 7, 15, 31, 63, 127, 255, 511) and not bool(st["act"].any()):
-                break  # (checked at a few points only: every check is a host sync)
-            lo, hi = _leaf_idx_to_ckpt_idxs(i)
-            ints[3], ints[4], ints[5] = i & 1, lo, hi
-            ptrs[22] = U[i].data_ptr()
-            _lib.check(pre(ptrs, ints, stream), "lslb_nuts_leaf_pre")
-            if self.f_into is not None:
-                self.f_into(st["q_n"], st["lp_n"], st["g_n"])
+        ints = (Ct.c_int * 6)(C, P, st["ck_r"].shape[1], 0, 0, 0)
+
+        def run_leaves(i0, i1):
+            stream = _lib.stream_ptr()
+            for i in range(i0, i1):
+                lo, hi = _leaf_idx_to_ckpt_idxs(i)
+                ints[3], ints[4], ints[5] = i & 1, lo, hi
+                ptrs[22] = st["U"][i].data_ptr()
+                _lib.check(pre(ptrs, ints, stream), "lslb_nuts_leaf_pre")
+                if self.f_into is not None:
+                    self.f_into(st["q_n"], st["lp_n"], st["g_n"])
+                else:
+                    lp, g = self.f(st["q_n"])
+                    st["lp_n"].copy_(lp); st["g_n"].copy_(g)
+                _lib.check(post(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+
+        # leaf ranges [0,1), [1,2), [2,4), [4,8), ...: between two ranges the host checks whether any
+        # chain is still active (every check is a host sync)
+        i0 = 0
+        while i0 < n_leaves:
+            i1 = 1 if i0 == 0 else min(2 * i0, n_leaves)
+            if i0 > 0 and not bool(st["act"].any()):
+                break
+            if self.use_graphs and self._graph_ready:
+                g = self._graphs.get(i0)
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        run_leaves(i0, i1)
+                    self._graphs[i0] = g  # (capturing does not execute: replay below)
+                g.replay()
             else:
-                lp, g = self.f(st["q_n"])
-                st["lp_n"].copy_(lp); st["g_n"].copy_(g)
-            self.evals += 1
-            _lib.check(post(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+                run_leaves(i0, i1)
+            self.evals += i1 - i0
+            i0 = i1
+        self._graph_ready = True  # the first subtree ran eagerly (lazy one-time initialisation done)
+        ck_r.copy_(st["ck_r"]); ck_s.copy_(st["ck_s"])
         return (st["q_e"].clone(), st["r_e"].clone(), st["g_e"].clone(), st["q_s"].clone(), st["lp_s"].clone(),
                 st["g_s"].clone(), st["logw_s"].clone(), st["rsum_s"].clone(), st["turn_s"].bool(),
                 st["div_s"].bool(), st["sum_acc"].clone(), st["n_leaf"].clone())

@@ -464,6 +464,28 @@ def test_nuts_fused_matches_torch_path(lb):
     assert int(i_ref.treedepth.max()) >= 3  # trajectories long enough to exercise the checkpoints
 
 
+def test_nuts_cuda_graphs_same_draws(lb):
+    """Replaying the leaf ranges from CUDA graphs changes launch overhead, not results."""
+    from liesel_b200.nuts import BatchedNUTS
+
+    spec, centre = synth.s3_gamlss(n=3000, k=8, dtype=np.float32)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 40)
+    q0, a = dev(th, plan), dev(aux, plan)
+    f = lambda q: plan.logp_grad(q.contiguous(), a)  # noqa: E731
+    into = lambda q, lp, g: plan.logp_grad(q, a, out=(lp, g))  # noqa: E731
+    kw = dict(seed=9, fused=True, initial_step_size=0.02, max_treedepth=6, logp_grad_into=into)
+    s_a = BatchedNUTS(f, q0, graphs=False, **kw)
+    s_b = BatchedNUTS(f, q0, graphs=True, **kw)
+    assert s_b.use_graphs
+    for _ in range(6):
+        i_a, i_b = s_a.transition(), s_b.transition()
+        assert torch.equal(i_a.treedepth, i_b.treedepth) and torch.equal(i_a.leapfrog, i_b.leapfrog)
+        assert torch.equal(s_a.q, s_b.q) and torch.equal(s_a.logp, s_b.logp)
+        assert i_a.evaluations == i_b.evaluations
+    assert len(s_b._graphs) >= 3  # several leaf ranges were captured and replayed
+
+
 # --- IWLS-within-Gibbs sampler: the reference's own kernel integration pins ------------------------
 def test_iwls_sampler_recovers_model_lm(lb, golden_dir):
     """tests/goose/kernels/test_iwls.py via model_lm.py:70-84: posterior means within 5 % of OLS,

@@ -26,6 +26,7 @@ ap.add_argument("--warmup", type=int, default=300)
 ap.add_argument("--samples", type=int, default=200)
 ap.add_argument("--cpu", action="store_true", help="CPU arm: oracle/cpu_port.py as the evaluator")
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--graphs", action="store_true", help="replay NUTS leaf ranges from CUDA graphs")
 ap.add_argument("--sampler", default="nuts", choices=["nuts", "iwls"],
                 help="nuts: one NUTS block + Gibbs tau2; iwls: IWLS per coefficient block + Gibbs tau2 "
                      "(what dist_reg_mcmc configures, model/distreg.py:300-349)")
@@ -123,7 +124,7 @@ if args.sampler == "iwls":
     }), flush=True)
     sys.exit(0)
 t0 = time.perf_counter()
-s = BatchedNUTS(f, q0, seed=args.seed, logp_grad_into=f_into)
+s = BatchedNUTS(f, q0, seed=args.seed, logp_grad_into=f_into, graphs=args.graphs and not args.cpu)
 winfo = s.warmup(args.warmup, hook=gibbs)
 sync()
 t1 = time.perf_counter()
