@@ -41,16 +41,20 @@ extern "C" {
 #define LSLB_VERSION 100
 #define LSLB_MAX_BLOCKS 16
 #define LSLB_MAX_IWLS_P 64
+#define LSLB_MAX_PEERS 16
+#define LSLB_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 typedef struct CUstream_st* lslb_stream_t; /* == cudaStream_t */
 typedef struct lslb_plan lslb_plan;
+typedef struct lslb_peer lslb_peer; /* peer-memory exchange group of the ranks of one box */
 
 enum lslb_status {
   LSLB_OK = 0,
   LSLB_ERR_INVALID = 1,     /* bad argument / unsupported model structure */
   LSLB_ERR_WORKSPACE = 2,   /* workspace too small */
   LSLB_ERR_CUDA = 3,        /* a CUDA runtime call failed (see lslb_last_cuda_error) */
-  LSLB_ERR_UNSUPPORTED = 4  /* valid request this build does not implement */
+  LSLB_ERR_UNSUPPORTED = 4, /* valid request this build does not implement */
+  LSLB_ERR_COMM = 5         /* NCCL missing or a collective failed (see lslb_last_cuda_error) */
 };
 
 enum lslb_dtype { LSLB_F32 = 0, LSLB_F64 = 1 };
@@ -197,6 +201,70 @@ int lslb_spline_basis_f32(const float* x, int64_t n, const float* knots, int nkn
                           int32_t* start, float* weights, lslb_stream_t stream);
 int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int nknots,
                           int32_t* start, double* weights, lslb_stream_t stream);
+
+/*
+ * Row sharding over the GPUs of one box (no counterpart in the reference, which has no
+ * multi-device path: src/liesel/goose/engine.py:442-448 is a vmap over chains on one device).
+ * Every rank builds its plan on ITS rows and evaluates ALL C chains; the partial sums of
+ * `_reduced_sum` (src/liesel/model/model.py:50-53), of its gradient and of the IWLS score /
+ * information are summed over ranks before the call returns (same stream, asynchronous).
+ * LSLB_SKIP_PRIOR is set internally on ranks > 0, so priors and constants enter once.
+ * All ranks must issue the same sequence of sharded calls with the same C / block.
+ *
+ * (1) Peer memory over NVLink/NVSwitch. The evaluation's finalize kernel writes its partials
+ * straight into an exchange buffer that every other rank has mapped through CUDA IPC; one more
+ * kernel publishes an epoch flag to all peers, waits for theirs and sums the W partials through
+ * P2P loads in RANK ORDER, so all ranks return bitwise identical values. No library, no host
+ * synchronisation. A peer group is used by one host thread at a time and its calls cannot be
+ * captured into a CUDA graph (LSLB_ERR_UNSUPPORTED while the stream is capturing).
+ *   lslb_peer_create : allocates this rank's buffer for results of up to `max_elems` elements
+ *                      (logp+grad: C*(P+1); IWLS: C*p*(p+1)) and writes its IPC handle
+ *                      (LSLB_PEER_HANDLE_BYTES, HOST memory) to `handle`; synchronous.
+ *   lslb_peer_connect: `handles` = the world's handles in rank order (HOST, world x 64 bytes),
+ *                      exchanged by the caller (e.g. torch.distributed.all_gather); maps the peers.
+ *   lslb_peer_timed_out: *timed_out != 0 when a wait for a peer exceeded ~2 s (results invalid);
+ *                      synchronous, for tests and diagnostics.
+ */
+int lslb_peer_create(int rank, int world, size_t max_elems, lslb_peer** out, void* handle);
+int lslb_peer_connect(lslb_peer* peer, const void* handles);
+void lslb_peer_destroy(lslb_peer* peer);
+int lslb_peer_timed_out(lslb_peer* peer, int* timed_out);
+int lslb_logp_grad_peer_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
+                            float* logp, float* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                            lslb_peer* peer, lslb_stream_t stream);
+int lslb_logp_grad_peer_f64(const lslb_plan* plan, int C, const double* params, const double* aux,
+                            double* logp, double* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                            lslb_peer* peer, lslb_stream_t stream);
+int lslb_iwls_peer_f32(const lslb_plan* plan, int C, int block, const float* params,
+                       const float* aux, float* score, float* info, float* chol, uint32_t flags,
+                       void* ws, size_t ws_bytes, lslb_peer* peer, lslb_stream_t stream);
+int lslb_iwls_peer_f64(const lslb_plan* plan, int C, int block, const double* params,
+                       const double* aux, double* score, double* info, double* chol,
+                       uint32_t flags, void* ws, size_t ws_bytes, lslb_peer* peer,
+                       lslb_stream_t stream);
+
+/*
+ * (2) NCCL. `comm` is an ncclComm_t of the caller (any NCCL 2.x; the symbols are resolved from
+ * the process's libnccl.so.2 at first use, LSLB_ERR_COMM if absent). logp/grad (score/info) are
+ * all-reduced in place with ncclSum on `stream`; chol is computed from the reduced information.
+ * lslb_nccl_unique_id / lslb_nccl_comm_create / _destroy wrap ncclGetUniqueId (128 bytes, HOST) /
+ * ncclCommInitRank / ncclCommDestroy for callers without an NCCL binding of their own.
+ */
+int lslb_nccl_unique_id(void* id128);
+int lslb_nccl_comm_create(int rank, int world, const void* id128, void** comm);
+void lslb_nccl_comm_destroy(void* comm);
+int lslb_logp_grad_nccl_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
+                            float* logp, float* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                            void* comm, lslb_stream_t stream);
+int lslb_logp_grad_nccl_f64(const lslb_plan* plan, int C, const double* params, const double* aux,
+                            double* logp, double* grad, uint32_t flags, void* ws, size_t ws_bytes,
+                            void* comm, lslb_stream_t stream);
+int lslb_iwls_nccl_f32(const lslb_plan* plan, int C, int block, const float* params,
+                       const float* aux, float* score, float* info, float* chol, uint32_t flags,
+                       void* ws, size_t ws_bytes, void* comm, lslb_stream_t stream);
+int lslb_iwls_nccl_f64(const lslb_plan* plan, int C, int block, const double* params,
+                       const double* aux, double* score, double* info, double* chol,
+                       uint32_t flags, void* ws, size_t ws_bytes, void* comm, lslb_stream_t stream);
 
 /*
  * Fused per-leaf bookkeeping of the batched NUTS driver (liesel_b200/nuts.py; the trajectory code

@@ -88,6 +88,32 @@ for _sfx in ("f32", "f64"):
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
 
 for _sfx in ("f32", "f64"):
+    # row-sharded variants: one more pointer (lslb_peer* / ncclComm_t) before the stream
+    for _tr in ("peer", "nccl"):
+        f = getattr(lib, f"lslb_logp_grad_{_tr}_{_sfx}")
+        f.restype = _i
+        f.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _u32, _vp, _sz, _vp, _vp]
+        f = getattr(lib, f"lslb_iwls_{_tr}_{_sfx}")
+        f.restype = _i
+        f.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _sz, _vp, _vp]
+lib.lslb_peer_create.restype = _i
+lib.lslb_peer_create.argtypes = [_i, _i, _sz, C.POINTER(_vp), _vp]
+lib.lslb_peer_connect.restype = _i
+lib.lslb_peer_connect.argtypes = [_vp, _vp]
+lib.lslb_peer_destroy.restype = None
+lib.lslb_peer_destroy.argtypes = [_vp]
+lib.lslb_peer_timed_out.restype = _i
+lib.lslb_peer_timed_out.argtypes = [_vp, C.POINTER(_i)]
+lib.lslb_nccl_unique_id.restype = _i
+lib.lslb_nccl_unique_id.argtypes = [_vp]
+lib.lslb_nccl_comm_create.restype = _i
+lib.lslb_nccl_comm_create.argtypes = [_i, _i, _vp, C.POINTER(_vp)]
+lib.lslb_nccl_comm_destroy.restype = None
+lib.lslb_nccl_comm_destroy.argtypes = [_vp]
+PEER_HANDLE_BYTES = 64
+NCCL_ID_BYTES = 128
+
+for _sfx in ("f32", "f64"):
     f = getattr(lib, "lslb_nuts_leaf_pre_" + _sfx)
     f.restype = _i
     f.argtypes = [C.POINTER(_vp), C.POINTER(_i), _vp]
@@ -105,6 +131,10 @@ lib.lslb_debug_tc_probe.restype = _i
 lib.lslb_debug_tc_probe.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
 
 EXPORTS = [
+    "lslb_peer_create", "lslb_peer_connect", "lslb_peer_destroy", "lslb_peer_timed_out",
+    "lslb_logp_grad_peer_f32", "lslb_logp_grad_peer_f64", "lslb_iwls_peer_f32", "lslb_iwls_peer_f64",
+    "lslb_nccl_unique_id", "lslb_nccl_comm_create", "lslb_nccl_comm_destroy",
+    "lslb_logp_grad_nccl_f32", "lslb_logp_grad_nccl_f64", "lslb_iwls_nccl_f32", "lslb_iwls_nccl_f64",
     "lslb_debug_tc_probe",
     "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
     "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
@@ -124,7 +154,7 @@ class LieselB200Error(RuntimeError):
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib.lslb_status_string(status).decode()
-        if status == 3:
+        if status in (3, 5):
             msg += ": " + lib.lslb_last_cuda_error().decode()
         raise LieselB200Error(f"{what} failed with status {status} ({msg})")
 

@@ -17,6 +17,7 @@ namespace lslb {
 // error plumbing: compute calls never abort, they return a status code
 // ---------------------------------------------------------------------------------------
 void set_cuda_error(cudaError_t e, const char* where);
+void set_comm_error(const char* msg);  // reported by lslb_last_cuda_error() as well
 void debug_record_start(cudaStream_t s);  // debug.cu: optional events around the dominant kernel
 void debug_record_stop(cudaStream_t s);
 #define LSLB_CUDA(call)                                  \

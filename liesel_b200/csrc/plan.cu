@@ -15,6 +15,8 @@ void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
 }
 
+void set_comm_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
 // fine chunk boundaries: fine[f] = f*n/F moved forward to the next group start
 __global__ void fine_bounds_kernel(long long n, int F, const int* __restrict__ gidx,
                                    long long* __restrict__ fine) {
@@ -88,6 +90,7 @@ extern "C" const char* lslb_status_string(int s) {
     case LSLB_ERR_WORKSPACE: return "workspace too small";
     case LSLB_ERR_CUDA: return "CUDA runtime error";
     case LSLB_ERR_UNSUPPORTED: return "not implemented for this configuration";
+    case LSLB_ERR_COMM: return "collective (NCCL) error";
     default: return "unknown status";
   }
 }

@@ -11,6 +11,12 @@ the computation:
   contiguous block of rows and ALL chains, evaluate with ``LSLB_SKIP_PRIOR`` on ranks > 0 and
   all-reduce ``[C, P+1]`` (:class:`RowSharded`). A random intercept is sharded by whole groups so its
   gradient needs no reduction (:func:`row_shard` with ``group_idx``).
+
+The sum over ranks can run inside the C call itself (``Plan.logp_grad(..., shard=...)``):
+:class:`PeerGroup` — the finalize kernel writes into an IPC-mapped exchange buffer and one kernel
+sums the ranks' partials through NVLink peer loads in rank order (bitwise identical on all ranks);
+:class:`NcclComm` — ``ncclAllReduce`` on a communicator owned by the library's caller.
+``torch.distributed`` is only the bootstrap that exchanges the 64-byte IPC handles / the NCCL id.
 """
 
 from __future__ import annotations
@@ -53,6 +59,88 @@ def row_shard(n: int, rank: int, world_size: int, group_idx: np.ndarray | None =
         for r in range(1, world_size + 1):
             bounds[r] = max(bounds[r], bounds[r - 1])
     return bounds[rank], bounds[rank + 1]
+
+
+def _exchange_bytes(payload: bytes, group=None) -> list[bytes]:
+    """All-gather of a small fixed-size host blob over ``torch.distributed`` (bootstrap only)."""
+    world = dist.get_world_size(group)
+    out: list = [None] * world
+    dist.all_gather_object(out, payload, group=group)
+    return out
+
+
+class PeerGroup:
+    """
+    Peer-memory exchange group of the ranks of one box (``lslb_peer_*`` in the C ABI).
+    ``max_elems`` = the largest result of a sharded call: ``C*(P+1)`` for logp+grad,
+    ``C*p*(p+1)`` for IWLS. All ranks must make the same sharded calls in the same order.
+    """
+
+    transport = "peer"
+
+    def __init__(self, max_elems: int, device: torch.device, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib = _lib
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
+        self.handle = C.c_void_p()
+        mine = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.lslb_peer_create(self.rank, self.world, int(max_elems),
+                                                 C.byref(self.handle), mine), "lslb_peer_create")
+            if self.world > 1:
+                blobs = _exchange_bytes(mine.raw, group)
+                _lib.check(_lib.lib.lslb_peer_connect(self.handle, C.c_char_p(b"".join(blobs))),
+                           "lslb_peer_connect")
+                dist.barrier(group)  # nobody publishes before every rank has mapped every buffer
+
+    def timed_out(self) -> bool:
+        import ctypes as C
+
+        flag = C.c_int(0)
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib.lslb_peer_timed_out(self.handle, C.byref(flag)), "lslb_peer_timed_out")
+        return bool(flag.value)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            with torch.cuda.device(self.device):
+                self._lib.lib.lslb_peer_destroy(self.handle)
+            self.handle.value = None
+
+
+class NcclComm:
+    """An ``ncclComm_t`` created through the library's own thin NCCL wrappers (``lslb_nccl_*``)."""
+
+    transport = "nccl"
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib = _lib
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
+        self.handle = C.c_void_p()
+        uid = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+        if self.rank == 0:
+            _lib.check(_lib.lib.lslb_nccl_unique_id(uid), "lslb_nccl_unique_id")
+        blob = _exchange_bytes(uid.raw, group)[0] if self.world > 1 else uid.raw
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.lslb_nccl_comm_create(self.rank, self.world, C.c_char_p(blob),
+                                                      C.byref(self.handle)), "lslb_nccl_comm_create")
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            with torch.cuda.device(self.device):
+                self._lib.lib.lslb_nccl_comm_destroy(self.handle)
+            self.handle.value = None
 
 
 class RowSharded:

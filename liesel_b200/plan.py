@@ -153,8 +153,12 @@ class Plan:
         return params.shape[0]
 
     # -- compute entry points -------------------------------------------------------
-    def logp_grad(self, params, aux=None, want_grad: bool = True, flags: int = 0, out=None):
-        """(logp [C], grad [C, P] or None) for C chains: one pass over the rows."""
+    def logp_grad(self, params, aux=None, want_grad: bool = True, flags: int = 0, out=None, shard=None):
+        """
+        (logp [C], grad [C, P] or None) for C chains: one pass over the rows. ``shard`` is a
+        ``dist.PeerGroup`` or ``dist.NcclComm`` when this plan holds one rank's rows: the partial
+        sums are then added over the ranks inside the same C call.
+        """
         Cn = self._check_inputs(params, aux)
         if out is None:
             logp = torch.empty(Cn, dtype=self.dtype, device=self.device)
@@ -163,14 +167,21 @@ class Plan:
             logp, grad = out
         ws = self.workspace(Cn)
         with torch.cuda.device(self.device):
-            fn = getattr(_lib.lib, "lslb_logp_grad_" + _lib.sfx(self.dtype))
-            _lib.check(fn(self._handle, Cn, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(logp),
-                          _lib.ptr(grad), flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
-                       "lslb_logp_grad")
+            if shard is None:
+                fn = getattr(_lib.lib, "lslb_logp_grad_" + _lib.sfx(self.dtype))
+                _lib.check(fn(self._handle, Cn, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(logp),
+                              _lib.ptr(grad), flags, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                           "lslb_logp_grad")
+            else:
+                fn = getattr(_lib.lib, f"lslb_logp_grad_{shard.transport}_" + _lib.sfx(self.dtype))
+                _lib.check(fn(self._handle, Cn, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(logp),
+                              _lib.ptr(grad), flags, _lib.ptr(ws), ws.numel(), shard.handle,
+                              _lib.stream_ptr()), "lslb_logp_grad_" + shard.transport)
         return logp, grad
 
-    def iwls(self, block: int | str, params, aux=None, want_chol: bool = True, flags: int = 0):
-        """(score [C,p], info [C,p,p], chol [C,p,p] or None) of one coefficient block."""
+    def iwls(self, block: int | str, params, aux=None, want_chol: bool = True, flags: int = 0, shard=None):
+        """(score [C,p], info [C,p,p], chol [C,p,p] or None) of one coefficient block; ``shard`` as in
+        :meth:`logp_grad` (the Cholesky factor is then taken of the information summed over ranks)."""
         Cn = self._check_inputs(params, aux)
         b = self.spec.block_index(block) if isinstance(block, str) else int(block)
         p = self.spec.blocks[b].ncoef
@@ -179,10 +190,16 @@ class Plan:
         chol = torch.empty((Cn, p, p), dtype=self.dtype, device=self.device) if want_chol else None
         ws = self.workspace(Cn)
         with torch.cuda.device(self.device):
-            fn = getattr(_lib.lib, "lslb_iwls_" + _lib.sfx(self.dtype))
-            _lib.check(fn(self._handle, Cn, b, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(score),
-                          _lib.ptr(info), _lib.ptr(chol), flags, _lib.ptr(ws), ws.numel(),
-                          _lib.stream_ptr()), "lslb_iwls")
+            if shard is None:
+                fn = getattr(_lib.lib, "lslb_iwls_" + _lib.sfx(self.dtype))
+                _lib.check(fn(self._handle, Cn, b, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(score),
+                              _lib.ptr(info), _lib.ptr(chol), flags, _lib.ptr(ws), ws.numel(),
+                              _lib.stream_ptr()), "lslb_iwls")
+            else:
+                fn = getattr(_lib.lib, f"lslb_iwls_{shard.transport}_" + _lib.sfx(self.dtype))
+                _lib.check(fn(self._handle, Cn, b, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(score),
+                              _lib.ptr(info), _lib.ptr(chol), flags, _lib.ptr(ws), ws.numel(),
+                              shard.handle, _lib.stream_ptr()), "lslb_iwls_" + shard.transport)
         return score, info, chol
 
     def quadform(self, block: int | str, params):

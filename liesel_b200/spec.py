@@ -286,6 +286,32 @@ class ModelSpec:
                 blk.tau2_slot = -1
         return self
 
+    def rows(self, start: int, stop: int) -> "ModelSpec":
+        """
+        The same model on rows ``[start, stop)`` only — one rank's share under row sharding
+        (``dist.row_shard``). Coefficient layout, priors, knots and group numbering are unchanged, so
+        per-rank partial results add up to the full evaluation. A centred spline needs its column
+        means fixed beforehand (they are means over ALL rows, not over the shard).
+        """
+        import copy
+
+        if not 0 <= start <= stop <= self.n:
+            raise ValueError("row range out of bounds")
+        part = copy.copy(self)
+        part.y = np.ascontiguousarray(self.y[start:stop])
+        part._predictors = dict(self._predictors)
+        part.blocks = []
+        for blk in self.blocks:
+            if blk.center and blk.colmean is None:
+                raise ValueError(f"block {blk.name!r}: fix the column means (center=<array>) before sharding rows")
+            nb = copy.copy(blk)
+            for attr in ("X", "x", "start", "weights", "idx"):
+                arr = getattr(blk, attr)
+                if arr is not None:
+                    setattr(nb, attr, np.ascontiguousarray(arr[start:stop]))
+            part.blocks.append(nb)
+        return part._relayout()
+
     @property
     def num_params(self) -> int:
         return sum(b.ncoef for b in self.blocks)

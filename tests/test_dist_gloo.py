@@ -95,3 +95,33 @@ def test_row_and_chain_sharding_world2():
     port = _free_port()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("cfg", ["s3c", "s5", "s2"])
+def test_spec_rows_partials_add_up(cfg):
+    """``ModelSpec.rows`` keeps layout/priors/knots: likelihood parts of the shards add up (fp64 oracle)."""
+    from oracle import splines as OS
+
+    if cfg == "s3c":
+        spec, centre = synth.s3_gamlss(n=3000, dtype=np.float64)
+    elif cfg == "s5":
+        spec, centre = synth.s5_poisson_ri(n=3000, G=90, dtype=np.float64, balanced=False)
+    else:
+        spec, centre = synth.s2_pspline_gam(n=2000, dtype=np.float64)
+    for blk in spec.blocks:  # bands and column means are fixed on the full data before sharding
+        if blk.kind == 1 and blk.start is None:
+            blk.start, blk.weights = OS.banded_basis(blk.x, blk.knots, blk.order)
+        if blk.kind == 1 and blk.center and blk.colmean is None:
+            blk.colmean = OS.band_to_dense(blk.start, np.asarray(blk.weights, dtype=np.float64), blk.ncoef).mean(axis=0)
+    th, aux = synth.evaluation_points(spec, centre, 3)
+    ref_lik = sam.log_prob_parts(spec, th, aux)["response"]
+    gidx = next((b.idx for b in spec.blocks if b.idx is not None), None)
+    acc = 0.0
+    for rank in range(3):
+        a, b = ld.row_shard(spec.n, rank, 3, gidx)
+        part = spec.rows(a, b)
+        assert part.num_params == spec.num_params and part.position_keys() == spec.position_keys()
+        acc = acc + sam.log_prob_parts(part, th, aux)["response"]
+    np.testing.assert_allclose(acc, ref_lik, rtol=1e-11)
+    with pytest.raises(ValueError):
+        spec.rows(5, spec.n + 1)
