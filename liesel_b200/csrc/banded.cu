@@ -311,11 +311,27 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.TC = x2 ? 256 : 128;  // chains per CTA
   k.Cpad = (C + k.TC - 1) / k.TC * k.TC;
   k.ntiles_chain = k.Cpad / k.TC;
+  if (x2) {
+    // Chain counts that leave the last 256-chain CTA at most half full (a sampler that drops
+    // finished chains calls with any C): 128-chain CTAs (2 warps) at twice the residency, so the
+    // cost follows ceil(C / 128). Measured on H: the warps of this kernel are latency-bound, an SM
+    // needs its 16 resident warps either way, and a CTA with idle or missing warps costs as much
+    // as a full one (3-warp CTAs: 0.56 ms at C = 576 against 0.62 ms for 768 chains).
+    k.tc_eff = 256;
+    const int rem = C % 256;
+    if (rem > 0 && rem <= 128) k.tc_eff = 128;
+    if (const char* e = getenv("LSLB_BANDED_TCEFF"))  // tuning knob: 128 / 256 forces the CTA size
+      if (atoi(e) == 128 || atoi(e) == 256) k.tc_eff = atoi(e);
+    k.Cpad = (C + k.tc_eff - 1) / k.tc_eff * k.tc_eff;
+    k.ntiles_chain = k.Cpad / k.tc_eff;
+  }
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
-  int ctas_per_sm = x2 ? 4 : 6;
+  int ctas_per_sm = x2 ? 512 / (k.tc_eff / 2) : 6;  // x2: 16 resident warps per SM (register budget)
   if (const char* e = getenv("LSLB_BANDED_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;  // tuning knob
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles_chain - 1) / k.ntiles_chain;
+  if (const char* e = getenv("LSLB_BANDED_WANT_FLOOR"))  // tuning knob: never exceed one resident wave
+    if (atoi(e) > 0) want = ((long long)plan->sm_count * ctas_per_sm) / k.ntiles_chain;
   if (want < 1) want = 1;
   if (want > k.ntiles_total) want = k.ntiles_total;
   k.tiles_per_cta = (int)((k.ntiles_total + want - 1) / want);

@@ -447,7 +447,9 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 // host ------------------------------------------------------------------------------------------
 template <int FAM, int NS, int PM>
 static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity) {
-  dim3 grid(k.ntiles_chain, k.nchunks), block(128);
+  // a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps): the kernel's index arithmetic
+  // and cooperative loads are written in terms of blockDim.x
+  dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff > 0 ? k.tc_eff / 2 : 128);
   if (unity) {
     if (g) banded_x2_kernel<FAM, NS, PM, true, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
     else banded_x2_kernel<FAM, NS, PM, false, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);

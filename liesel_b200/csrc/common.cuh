@@ -251,6 +251,7 @@ struct LaunchCfg {
 LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain, size_t smem_fixed = 0);
 struct BandedCfg {
   int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
+  int tc_eff = 0;  // banded_x2: chains a CTA really owns (multiple of 64, <= TC); 0 = TC
 };
 struct TcCfg {
   int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;

@@ -80,7 +80,8 @@ class BatchedNUTS:
                  da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
                  da_t0: int = 10, divergence_threshold: float = 1000.0, seed: int = 0,
                  initial_step_size: float | None = None, fused: bool | None = None,
-                 logp_grad_into: Callable | None = None, graphs: bool = False):
+                 logp_grad_into: Callable | None = None, graphs: bool = False, compact: bool = False,
+                 compact_below: float = 0.8):
         """
         ``fused`` (default: on for CUDA tensors): run the per-leaf bookkeeping in the two CUDA kernels
         ``lslb_nuts_leaf_pre/post`` instead of ~30 torch ops. ``logp_grad_into(q, logp_out, grad_out)``
@@ -89,6 +90,14 @@ class BatchedNUTS:
         CUDA graphs, one graph per leaf range [2^(k-1), 2^k) (the ranges between two host-side "is any
         chain still active" checks), captured on first use; every leaf is five kernel launches, so
         at small n the launch latency, not the kernels, bounds a transition.
+        ``compact`` (needs ``fused`` and a ``logp_grad_into(q, logp_out, grad_out, chains=idx)`` that
+        accepts the indices of the chains it is given): chains whose tree has already terminated are
+        dropped from the batch — at every doubling, and inside a subtree at the host checks between
+        leaf ranges, the still-running chains are gathered into a dense batch (padded to a multiple of
+        64) whenever that batch is at most ``compact_below`` of the current one. The reference cannot do
+        this under ``jax.vmap`` (every chain pays for the deepest tree of the batch); here the
+        evaluation kernel's time is proportional to the chains it is given, so the saving is real.
+        The draws are those of the uncompacted driver up to float reduction order.
         """
         self.f = logp_grad_fn
         self.f_into = logp_grad_into
@@ -96,6 +105,9 @@ class BatchedNUTS:
         self.use_graphs = bool(graphs) and self.fused and logp_grad_into is not None
         self._graphs: dict = {}
         self._graph_ready = False
+        self.compact = bool(compact) and self.fused and logp_grad_into is not None and not self.use_graphs
+        self.compact_below = float(compact_below)
+        self.chain_evals = 0  # chain-evaluations actually computed inside subtrees (compaction metric)
         self.q = q0.clone()
         self.C, self.P = q0.shape
         self.dev, self.dt = q0.device, q0.dtype
@@ -200,16 +212,44 @@ class BatchedNUTS:
             st["ck_r"] = torch.empty((C, self.max_treedepth + 1, P), dtype=dt, device=dev)
             st["ck_s"] = torch.empty_like(st["ck_r"])
             self._fused_state = st
-        st["q_e"].copy_(q_e); st["r_e"].copy_(r_e); st["g_e"].copy_(g_e)
-        st["q_s"].copy_(q_e); st["g_s"].copy_(g_e); st["lp_s"].copy_(lp_prop)
-        st["logw_s"].fill_(-float("inf")); st["rsum_s"].zero_()
-        st["sum_acc"].zero_(); st["n_leaf"].zero_()
-        st["eps"].copy_(eps); st["h0"].copy_(h0)
-        st["act"].copy_(alive.to(torch.uint8)); st["turn_s"].zero_(); st["div_s"].zero_()
-        st["inv_mass"].copy_(self.inv_mass)
         n_leaves = 2 ** j
-        st["U"][:n_leaves].copy_(U)
-        st["ck_r"].copy_(ck_r); st["ck_s"].copy_(ck_s)
+        # -- which chains enter the batch ----------------------------------------------------------
+        idx, n_real, Cb = None, C, C  # idx: batch row -> chain; rows >= n_real are inactive padding
+        if self.compact:
+            sel = alive.nonzero().squeeze(1)
+            n_alive = int(sel.numel())
+            padded = -(-max(n_alive, 1) // 64) * 64
+            if padded <= self.compact_below * C:
+                idx, n_real, Cb = sel, n_alive, padded
+        out_keys2 = ("q_e", "r_e", "g_e", "q_s", "g_s", "rsum_s")
+        out_keys1 = ("lp_s", "logw_s", "sum_acc", "n_leaf", "turn_s", "div_s")
+        if idx is None:
+            st["q_e"].copy_(q_e); st["r_e"].copy_(r_e); st["g_e"].copy_(g_e)
+            st["q_s"].copy_(q_e); st["g_s"].copy_(g_e); st["lp_s"].copy_(lp_prop)
+            st["eps"].copy_(eps); st["h0"].copy_(h0)
+            st["act"].copy_(alive.to(torch.uint8))
+            st["inv_mass"].copy_(self.inv_mass)
+            st["U"][:n_leaves].copy_(U)
+            st["ck_r"].copy_(ck_r); st["ck_s"].copy_(ck_s)
+            full = None
+        else:
+            gidx = idx if n_real == Cb else torch.cat([idx, idx[:1].expand(Cb - n_real)])
+            for k, src in (("q_e", q_e), ("r_e", r_e), ("g_e", g_e), ("q_s", q_e), ("g_s", g_e),
+                           ("lp_s", lp_prop), ("eps", eps), ("h0", h0), ("inv_mass", self.inv_mass)):
+                torch.index_select(src, 0, gidx, out=st[k][:Cb])
+            st["act"][:n_real].fill_(1)
+            st["act"][n_real:Cb].zero_()
+            st["U"][:n_leaves, :Cb] = U.index_select(1, gidx)
+            # results of chains that are not in the batch: untouched edge state, empty subtree
+            full = {"q_e": q_e.clone(), "r_e": r_e.clone(), "g_e": g_e.clone(), "q_s": q_e.clone(),
+                    "g_s": g_e.clone(), "rsum_s": torch.zeros_like(q_e), "lp_s": lp_prop.clone(),
+                    "logw_s": torch.full((C,), -float("inf"), dtype=dt, device=dev),
+                    "sum_acc": torch.zeros(C, dtype=dt, device=dev), "n_leaf": torch.zeros(C, dtype=dt, device=dev),
+                    "turn_s": torch.zeros(C, dtype=torch.uint8, device=dev),
+                    "div_s": torch.zeros(C, dtype=torch.uint8, device=dev)}
+        st["logw_s"][:Cb].fill_(-float("inf")); st["rsum_s"][:Cb].zero_()
+        st["sum_acc"][:Cb].zero_(); st["n_leaf"][:Cb].zero_()
+        st["turn_s"][:Cb].zero_(); st["div_s"][:Cb].zero_()
         sfx = _lib.sfx(dt)
         pre = getattr(_lib.lib, "lslb_nuts_leaf_pre_" + sfx)
         post = getattr(_lib.lib, "lslb_nuts_leaf_post_" + sfx)
@@ -218,7 +258,7 @@ class BatchedNUTS:
                                          st["logw_s"], st["rsum_s"], st["ck_r"], st["ck_s"], st["sum_acc"],
                                          st["n_leaf"], st["act"], st["turn_s"], st["div_s"], st["U"]]
         ptrs = (Ct.c_void_p * 23)(*[t.data_ptr() for t in tens])
-        ints = (Ct.c_int * 6)(C, P, st["ck_r"].shape[1], 0, 0, 0)
+        ints = (Ct.c_int * 6)(Cb, P, st["ck_r"].shape[1], 0, 0, 0)
 
         def run_leaves(i0, i1):
             stream = _lib.stream_ptr()
@@ -228,19 +268,53 @@ class BatchedNUTS:
                 ptrs[22] = st["U"][i].data_ptr()
                 _lib.check(pre(ptrs, ints, stream), "lslb_nuts_leaf_pre")
                 if self.f_into is not None:
-                    self.f_into(st["q_n"], st["lp_n"], st["g_n"])
+                    if idx is None:
+                        self.f_into(st["q_n"], st["lp_n"], st["g_n"])
+                    else:
+                        self.f_into(st["q_n"][:Cb], st["lp_n"][:Cb], st["g_n"][:Cb], chains=gidx)
                 else:
                     lp, g = self.f(st["q_n"])
                     st["lp_n"].copy_(lp); st["g_n"].copy_(g)
                 _lib.check(post(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+
+        def flush():
+            """Results of the current batch rows -> full-size outputs (real rows only)."""
+            for k in out_keys2 + out_keys1:
+                full[k].index_copy_(0, idx, st[k][:n_real])
 
         # leaf ranges [0,1), [1,2), [2,4), [4,8), ...: between two ranges the host checks whether any
         # chain is still active (every check is a host sync)
         i0 = 0
         while i0 < n_leaves:
             i1 = 1 if i0 == 0 else min(2 * i0, n_leaves)
-            if i0 > 0 and not bool(st["act"].any()):
-                break
+            if i0 > 0:
+                if idx is None and not self.compact:
+                    if not bool(st["act"].any()):
+                        break
+                else:
+                    keep = st["act"][:n_real].nonzero().squeeze(1)
+                    n_keep = int(keep.numel())
+                    if n_keep == 0:
+                        break
+                    padded = -(-n_keep // 64) * 64
+                    if self.compact and i1 - i0 >= 4 and padded <= self.compact_below * Cb:
+                        # drop the chains whose subtree already terminated: their results are final
+                        if idx is None:
+                            idx = torch.arange(C, device=dev)
+                            full = {k: st[k].clone() for k in out_keys2 + out_keys1}
+                        else:
+                            flush()
+                        gk = keep if n_keep == padded else torch.cat([keep, keep[:1].expand(padded - n_keep)])
+                        for k in ("q_e", "r_e", "g_e", "q_s", "g_s", "rsum_s", "inv_mass", "lp_s", "logw_s",
+                                  "sum_acc", "n_leaf", "eps", "h0", "turn_s", "div_s", "ck_r", "ck_s"):
+                            st[k][:padded] = st[k].index_select(0, gk)
+                        st["U"][i0:n_leaves, :padded] = st["U"][i0:n_leaves].index_select(1, gk)
+                        st["act"][:n_keep].fill_(1)
+                        st["act"][n_keep:padded].zero_()
+                        idx = idx.index_select(0, keep)
+                        n_real, Cb = n_keep, padded
+                        gidx = idx if n_real == Cb else torch.cat([idx, idx[:1].expand(Cb - n_real)])
+                        ints[0] = Cb
             if self.use_graphs and self._graph_ready:
                 g = self._graphs.get(i0)
                 if g is None:
@@ -252,12 +326,18 @@ class BatchedNUTS:
             else:
                 run_leaves(i0, i1)
             self.evals += i1 - i0
+            self.chain_evals += (i1 - i0) * Cb
             i0 = i1
         self._graph_ready = True  # the first subtree ran eagerly (lazy one-time initialisation done)
-        ck_r.copy_(st["ck_r"]); ck_s.copy_(st["ck_s"])
-        return (st["q_e"].clone(), st["r_e"].clone(), st["g_e"].clone(), st["q_s"].clone(), st["lp_s"].clone(),
-                st["g_s"].clone(), st["logw_s"].clone(), st["rsum_s"].clone(), st["turn_s"].bool(),
-                st["div_s"].bool(), st["sum_acc"].clone(), st["n_leaf"].clone())
+        if idx is None:
+            ck_r.copy_(st["ck_r"]); ck_s.copy_(st["ck_s"])
+            res = st
+            cl = lambda k: st[k].clone()
+        else:
+            flush()  # (checkpoints are scratch of ONE subtree: nothing to hand back)
+            cl = lambda k: full[k]
+        return (cl("q_e"), cl("r_e"), cl("g_e"), cl("q_s"), cl("lp_s"), cl("g_s"), cl("logw_s"), cl("rsum_s"),
+                cl("turn_s").bool(), cl("div_s").bool(), cl("sum_acc"), cl("n_leaf"))
 
     # -- one NUTS transition for all chains ---------------------------------------------------
     @torch.no_grad()

@@ -34,6 +34,8 @@ class Plan:
         self.dtype = _TORCH[np.dtype(spec.dtype)]
         self._keep: list[torch.Tensor] = []
         self._ws: dict[int, torch.Tensor] = {}
+        self._ws_bytes: dict[int, int] = {}
+        self._ws_retired: list[torch.Tensor] = []  # outgrown buffers stay alive (captured CUDA graphs)
         self._handle = C.c_void_p()
         dev, dt = self.device, self.dtype
 
@@ -136,11 +138,18 @@ class Plan:
 
     # -- workspace ------------------------------------------------------------------
     def workspace(self, C_: int) -> torch.Tensor:
-        ws = self._ws.get(C_)
-        if ws is None:
-            nbytes = _lib.lib.lslb_workspace_bytes(self._handle, C_)
-            ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
-            self._ws[C_] = ws
+        """One scratch buffer per plan, grown to the largest chain count seen (a batched sampler that
+        drops finished chains calls with many different C)."""
+        need = self._ws_bytes.get(C_)
+        if need is None:
+            need = max(int(_lib.lib.lslb_workspace_bytes(self._handle, C_)), 256)
+            self._ws_bytes[C_] = need
+        ws = self._ws.get(0)
+        if ws is None or ws.numel() < need:
+            if ws is not None:
+                self._ws_retired.append(ws)
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[0] = ws
         return ws
 
     def _check_inputs(self, params: torch.Tensor, aux: torch.Tensor | None):

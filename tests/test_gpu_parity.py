@@ -464,6 +464,43 @@ def test_nuts_fused_matches_torch_path(lb):
     assert int(i_ref.treedepth.max()) >= 3  # trajectories long enough to exercise the checkpoints
 
 
+def test_nuts_compaction_same_draws(lb):
+    """Dropping terminated chains from the batch changes the cost, not the draws (fp64: the only
+    difference is the reduction order of a smaller batch)."""
+    from liesel_b200.nuts import BatchedNUTS
+
+    spec, centre = synth.s3_gamlss(n=3000, k=8, dtype=np.float64)
+    plan = lb.Plan(spec)
+    C = 200
+    th, aux = synth.evaluation_points(spec, centre, C)
+    q0, a = dev(th, plan), dev(aux, plan)
+    f = lambda q: plan.logp_grad(q.contiguous(), a)
+
+    def into(q, lp, g, chains=None):
+        plan.logp_grad(q, a if chains is None else a.index_select(0, chains).contiguous(), out=(lp, g))
+
+    kw = dict(seed=11, fused=True, initial_step_size=0.02, max_treedepth=7, logp_grad_into=into)
+    s_ref = BatchedNUTS(f, q0, **kw)
+    s_cmp = BatchedNUTS(f, q0, compact=True, **kw)
+    assert s_cmp.compact and not s_ref.compact
+    # heterogeneous step sizes -> heterogeneous tree depths, as after per-chain adaptation
+    eps = 0.004 * torch.pow(torch.tensor(2.0, device=plan.device, dtype=q0.dtype),
+                            torch.arange(C, device=plan.device, dtype=q0.dtype) % 5)
+    s_ref.step_size, s_cmp.step_size = eps.clone(), eps.clone()
+    for _ in range(4):
+        i_ref, i_cmp = s_ref.transition(), s_cmp.transition()
+        assert torch.equal(i_ref.treedepth, i_cmp.treedepth)
+        assert torch.equal(i_ref.error_code, i_cmp.error_code)
+        assert torch.equal(i_ref.leapfrog, i_cmp.leapfrog)
+        np.testing.assert_allclose(i_cmp.acceptance_prob.cpu().numpy(), i_ref.acceptance_prob.cpu().numpy(),
+                                   rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(s_cmp.q.cpu().numpy(), s_ref.q.cpu().numpy(), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(s_cmp.logp.cpu().numpy(), s_ref.logp.cpu().numpy(), rtol=1e-10)
+    depths = i_ref.treedepth
+    assert int(depths.max()) > int(depths.min())  # the batch really was heterogeneous
+    assert s_cmp.evals == s_ref.evals and s_cmp.chain_evals < 0.9 * s_ref.chain_evals
+
+
 def test_nuts_cuda_graphs_same_draws(lb):
     """Replaying the leaf ranges from CUDA graphs changes launch overhead, not results."""
     from liesel_b200.nuts import BatchedNUTS

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=1.0, help="scales n (and G)")
 ap.add_argument("--configs", default="s1,s2,s3,h,s4,s5")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--chain-sweep", default="", help="comma-separated chain counts: time the H model at each")
 args = ap.parse_args()
 
 CFG = {
@@ -50,6 +51,18 @@ def timeit(fn, reps):
         ts.append(a.elapsed_time(b))
     return float(np.median(ts))
 
+
+if args.chain_sweep:
+    spec, centre = synth.s3_gamlss(n=int(1_000_000 * args.scale))
+    plan = Plan(spec)
+    rows = []
+    for C in [int(c) for c in args.chain_sweep.split(",")]:
+        th, aux = synth.evaluation_points(spec, centre, C)
+        t, a = torch.as_tensor(th, device="cuda"), torch.as_tensor(aux, device="cuda")
+        ms = timeit(lambda: plan.logp_grad(t, a), args.reps)
+        rows.append({"chains": C, "logp_grad_ms": ms, "us_per_chain": 1e3 * ms / C})
+    print(json.dumps({"config": "h_chain_sweep", "n": spec.n, "variant": plan.variant, "sweep": rows}), flush=True)
+    sys.exit(0)
 
 for name in args.configs.split(","):
     make, C, iwls_block = CFG[name]

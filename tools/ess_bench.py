@@ -27,6 +27,8 @@ ap.add_argument("--samples", type=int, default=200)
 ap.add_argument("--cpu", action="store_true", help="CPU arm: oracle/cpu_port.py as the evaluator")
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--graphs", action="store_true", help="replay NUTS leaf ranges from CUDA graphs")
+ap.add_argument("--compact", action="store_true",
+                help="drop chains whose tree has terminated from the batched evaluation")
 ap.add_argument("--sampler", default="nuts", choices=["nuts", "iwls"],
                 help="nuts: one NUTS block + Gibbs tau2; iwls: IWLS per coefficient block + Gibbs tau2 "
                      "(what dist_reg_mcmc configures, model/distreg.py:300-349)")
@@ -66,8 +68,16 @@ else:
     def f(q):
         return plan.logp_grad(q.contiguous(), aux)
 
-    def f_into(q, lp, g):
-        plan.logp_grad(q, aux, out=(lp, g))
+    _sel = {"chains": None, "aux": None}
+
+    def f_into(q, lp, g, chains=None):
+        """``chains``: indices of the chains in this (compacted) batch — picks their tau2 rows."""
+        if chains is None:
+            plan.logp_grad(q, aux, out=(lp, g))
+            return
+        if _sel["chains"] is not chains:
+            _sel["chains"], _sel["aux"] = chains, aux.index_select(0, chains).contiguous()
+        plan.logp_grad(q, _sel["aux"], out=(lp, g))
 
     def quad(blk, q):
         return plan.quadform(blk.name, q.contiguous()).double()
@@ -124,7 +134,8 @@ if args.sampler == "iwls":
     }), flush=True)
     sys.exit(0)
 t0 = time.perf_counter()
-s = BatchedNUTS(f, q0, seed=args.seed, logp_grad_into=f_into, graphs=args.graphs and not args.cpu)
+s = BatchedNUTS(f, q0, seed=args.seed, logp_grad_into=f_into, graphs=args.graphs and not args.cpu,
+                compact=args.compact and not args.cpu)
 winfo = s.warmup(args.warmup, hook=gibbs)
 sync()
 t1 = time.perf_counter()
@@ -149,6 +160,8 @@ out = {
     "ess_per_sec_incl_warmup": float(ess.min() / (t2 - t0)),
     "evals_posterior": int(s.evals - ev_w), "evals_warmup": int(ev_w),
     "batched_evals_per_sec_posterior": (s.evals - ev_w) / (t2 - t1),
+    "compact": bool(s.compact), "chain_evals_total": int(s.chain_evals),
+    "mean_batch_fill": float(s.chain_evals) / max(1.0, float(s.evals) * C),
     "mean_treedepth": float(np.mean([float(i.treedepth.float().mean()) for i in infos])),
     "max_treedepth_seen": int(max(int(i.treedepth.max()) for i in infos)),
     "mean_accept": float(np.mean([float(i.acceptance_prob.mean()) for i in infos])),
