@@ -312,22 +312,24 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.Cpad = (C + k.TC - 1) / k.TC * k.TC;
   k.ntiles_chain = k.Cpad / k.TC;
   if (x2) {
-    // Chain counts that leave the last 256-chain CTA at most half full (a sampler that drops
-    // finished chains calls with any C): 128-chain CTAs (2 warps) at twice the residency, so the
-    // cost follows ceil(C / 128). Measured on H: the warps of this kernel are latency-bound, an SM
-    // needs its 16 resident warps either way, and a CTA with idle or missing warps costs as much
-    // as a full one (3-warp CTAs: 0.56 ms at C = 576 against 0.62 ms for 768 chains).
-    k.tc_eff = 256;
-    const int rem = C % 256;
-    if (rem > 0 && rem <= 128) k.tc_eff = 128;
-    if (const char* e = getenv("LSLB_BANDED_TCEFF"))  // tuning knob: 128 / 256 forces the CTA size
-      if (atoi(e) == 128 || atoi(e) == 256) k.tc_eff = atoi(e);
-    k.Cpad = (C + k.tc_eff - 1) / k.tc_eff * k.tc_eff;
-    k.ntiles_chain = k.Cpad / k.tc_eff;
+    // banded_x2: ONE CTA of up to 16 warps (1024 chains) per SM whose warps share the staged row
+    // tiles and drift at most LSLB_X2_STAGES tiles apart; chains are spread evenly over the chain
+    // tiles in whole warps (64 chains), and with few chains several CTAs share an SM so that it
+    // still holds ~16 warps. (A sampler that drops finished chains calls with any C.)
+    k.ntiles_chain = (C + 1023) / 1024;
+    const int per_tile = (C + k.ntiles_chain - 1) / k.ntiles_chain;
+    k.tc_eff = (per_tile + 63) / 64 * 64;
+    if (const char* e = getenv("LSLB_BANDED_TCEFF"))  // tuning knob: chains per CTA (multiple of 64)
+      if (atoi(e) >= 64 && atoi(e) <= 1024 && atoi(e) % 64 == 0) {
+        k.tc_eff = atoi(e);
+        k.ntiles_chain = (C + k.tc_eff - 1) / k.tc_eff;
+      }
+    k.Cpad = k.ntiles_chain * k.tc_eff;
   }
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
-  int ctas_per_sm = x2 ? 512 / (k.tc_eff / 2) : 6;  // x2: 16 resident warps per SM (register budget)
+  int ctas_per_sm = x2 ? 16 / (k.tc_eff / 64) : 6;  // x2: at most 16 resident warps per SM (registers)
+  if (ctas_per_sm > 5) ctas_per_sm = 5;             // shared memory: 34 KB of row stages per CTA
   if (const char* e = getenv("LSLB_BANDED_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;  // tuning knob
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles_chain - 1) / k.ntiles_chain;
   if (const char* e = getenv("LSLB_BANDED_WANT_FLOOR"))  // tuning knob: never exceed one resident wave

@@ -24,6 +24,21 @@
 
 namespace lslb {
 
+#ifdef LSLB_X2_TRACE
+// Investigation build only (NVCC_EXTRA=-DLSLB_X2_TRACE): per-CTA start/end times and SM ids.
+__device__ unsigned long long g_x2_trace[8192][6];
+__device__ __forceinline__ unsigned long long x2_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned x2_smid() {
+  unsigned s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
+}
+#endif
+
 // PM: bit m set <=> smooth m feeds predictor 1 (log scale)
 // UNITY: every row's four weights sum to one (all x inside the knot range; checked at plan creation).
 // Then, over a run of equal spans, eta = b1 + sum_{u != 1} w_u (b_u - b1) and the gradient of b1 is
@@ -32,24 +47,32 @@ template <int FAM, int NS, int PM, bool GRAD, bool UNITY>
 #ifndef LSLB_X2_NRB
 #define LSLB_X2_NRB 4   // rows per register block (4 or 2)
 #endif
-#ifndef LSLB_X2_MINB
-#define LSLB_X2_MINB 4  // resident CTAs per SM the register budget is set for
+#ifndef LSLB_X2_STAGES
+#define LSLB_X2_STAGES 6  // ring depth: how many tiles the fastest warp of a CTA may run ahead of the slowest
 #endif
-__global__ void __launch_bounds__(128, LSLB_X2_MINB)
+__global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA (or 2 x 8, 4 x 4 for few chains)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
-  __shared__ __align__(128) XRaw<NS> raw[XSTAGES];
-  __shared__ __align__(8) u64 full[XSTAGES];
+  constexpr int X2S = LSLB_X2_STAGES;
+  __shared__ __align__(128) XRaw<NS> raw[X2S];
+  __shared__ __align__(8) u64 full[X2S];
+  __shared__ int done[X2S];  // warps that have finished with the tile in stage s
 
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
   const int ch = blockIdx.y;
   const int tile0 = ch * tiles_per_cta;
   const int my_tiles = min(tile0 + tiles_per_cta, ntiles_total) - tile0;
+#ifdef LSLB_X2_TRACE
+  unsigned long long tr_t0 = x2_gtime();
+  int tr_nonuni = 0;
+#endif
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < XSTAGES; ++s)
+    for (int s = 0; s < X2S; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&full[s])));
+      done[s] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -90,7 +113,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   };
 
   if (tid == 0) {
-    for (int k = 0; k < XSTAGES - 1 && k < my_tiles; ++k)
+    for (int k = 0; k < X2S && k < my_tiles; ++k)
       if (tile_rows(tile0 + k) == XR) issue(tile0 + k, k);
   }
 
@@ -184,16 +207,13 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
   for (int k = 0; k < my_tiles; ++k) {
     const int t = tile0 + k;
-    const int s = k % XSTAGES;
+    const int s = k % X2S;
     const int rows = tile_rows(t);
-    {  // refill the stage consumed in the previous iteration (every thread passed its barrier)
-      const int kn = k + XSTAGES - 1;
-      if (tid == 0 && kn < my_tiles && tile_rows(tile0 + kn) == XR) issue(tile0 + kn, kn % XSTAGES);
-    }
     XRaw<NS>& D = raw[s];
     if (rows == XR) {
-      wait_full(s, (k / XSTAGES) & 1);
-    } else {  // ragged last tile: ordinary loads (bulk copies need 16-byte multiples)
+      wait_full(s, (k / X2S) & 1);
+    } else {  // ragged last tile of the data: ordinary loads (bulk copies need 16-byte multiples)
+      __syncthreads();  // every warp has left the tile that used this stage before
       const long long r0 = (long long)t * XR;
       for (int r = tid; r < rows; r += blockDim.x) {
         D.y[r] = p.y[r0 + r];
@@ -338,6 +358,9 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     using N4 = std::integral_constant<int, LSLB_X2_NRB>;
     constexpr int NRB = LSLB_X2_NRB;
 
+#ifdef LSLB_X2_TRACE
+    tr_nonuni += uni ? 0 : 1;
+#endif
     const bool want_fast = UNITY && uni && rows == XR;
     if (want_fast != fastmode) {  // the accumulators change form: write them out in the old form
 #pragma unroll
@@ -432,9 +455,37 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       const float nr = -(float)rows;
       sr1 = add2(sr1, add2(sz2, pk(nr, nr)));  // sum (z^2 - 1)
     }
-    __syncthreads();  // everyone is done with stage s: it may be refilled
+    // The warps of a CTA are NOT synchronised per tile: whichever warp is the last to finish with
+    // stage s refills it. (With a barrier here — or with several small CTAs per SM — the hardware's
+    // oldest-first warp scheduling lets some warps finish the whole chunk at 45 % of the kernel's
+    // duration while the rest of the SM runs under-occupied: measured CTA durations 326..755 us.)
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(&done[s], 1) == (int)(blockDim.x >> 5) - 1) {
+        done[s] = 0;
+        const int kn = k + X2S;
+        if (kn < my_tiles && tile_rows(tile0 + kn) == XR) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(tile0 + kn, s);
+        }
+      }
+    }
   }
 
+#ifdef LSLB_X2_TRACE
+  if (tid == 0) {
+    const int id = blockIdx.y * gridDim.x + blockIdx.x;
+    if (id < 8192) {
+      g_x2_trace[id][0] = x2_smid();
+      g_x2_trace[id][1] = tr_t0;
+      g_x2_trace[id][2] = x2_gtime();
+      g_x2_trace[id][3] = blockIdx.x;
+      g_x2_trace[id][4] = blockIdx.y;
+      g_x2_trace[id][5] = ((unsigned long long)my_tiles << 32) | (unsigned)tr_nonuni;
+    }
+  }
+#endif
   if constexpr (GRAD) {
 #pragma unroll
     for (int m = 0; m < NS; ++m) flush(m);
@@ -449,7 +500,7 @@ template <int FAM, int NS, int PM>
 static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity) {
   // a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps): the kernel's index arithmetic
   // and cooperative loads are written in terms of blockDim.x
-  dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff > 0 ? k.tc_eff / 2 : 128);
+  dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff / 2);
   if (unity) {
     if (g) banded_x2_kernel<FAM, NS, PM, true, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
     else banded_x2_kernel<FAM, NS, PM, false, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
@@ -488,3 +539,10 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
 }
 
 }  // namespace lslb
+
+#ifdef LSLB_X2_TRACE
+extern "C" int lslb_debug_x2_trace(unsigned long long* out_host, int rows) {
+  if (rows > 8192) rows = 8192;
+  return cudaMemcpyFromSymbol(out_host, lslb::g_x2_trace, (size_t)rows * 6 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 3;
+}
+#endif
