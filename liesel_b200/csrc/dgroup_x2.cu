@@ -22,11 +22,15 @@ struct GRaw {
   int g[XR];
 };
 
+// One CTA of up to 16 warps (1024 chains) per SM; its warps share the staged tiles and are NOT
+// synchronised per tile: the last warp to leave a stage refills it (see banded_x2.cu for why).
 template <int PD, int FAM, bool GROUP, bool GRAD>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(512, 1)
 dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
+  constexpr int XSTAGES = PD > 8 ? 4 : 6;  // (shadows the 3-stage default of x2_common.cuh)
   __shared__ __align__(128) GRaw<PD> raw[XSTAGES];
   __shared__ __align__(8) u64 full[XSTAGES];
+  __shared__ int done[XSTAGES];
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);
   const int ch = blockIdx.y;
@@ -38,8 +42,10 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < XSTAGES; ++s)
+    for (int s = 0; s < XSTAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(x_smem_u32(&full[s])));
+      done[s] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -75,7 +81,7 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
     }
   };
   if (tid == 0) {
-    for (int k = 0; k < XSTAGES - 1 && k < my_tiles; ++k)
+    for (int k = 0; k < XSTAGES && k < my_tiles; ++k)
       if (tile_rows(tile0 + k) == XR) issue(tile0 + k, k);
   }
 
@@ -85,33 +91,35 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
   auto at2 = [&](int j) -> u64* { return reinterpret_cast<u64*>(mine + (size_t)j * ldc); };
   const u64 ZERO = pk(0.f, 0.f);
 
+  const u64 LOG2E = pk(1.4426950408889634f, 1.4426950408889634f);
+  const u64 NEG1 = pk(-1.f, -1.f);
+  const u64 INVS = pk(p.fixed_inv_scale, p.fixed_inv_scale);
+  // Poisson: the predictor is carried as log2(e) * eta (coefficients, offset and group effect are
+  // scaled when they are loaded), so the mean is a bare ex2 and sum(y eta) is rescaled per tile
   u64 b[PD], g[PD];
 #pragma unroll
   for (int j = 0; j < PD; ++j) {
     b[j] = j < D.p ? ld2(D.soff + j) : ZERO;
+    if constexpr (FAM == FAM_POISSON) b[j] = mul2(b[j], LOG2E);
     g[j] = ZERO;
   }
   u64 off = ZERO;
   for (int q = 0; q < p.ni; ++q) off = add2(off, ld2(p.ic[q].soff));
+  if constexpr (FAM == FAM_POISSON) off = mul2(off, LOG2E);
   int curg = -1;
-  u64 bg = ZERO, accg = ZERO, sd = ZERO;
+  u64 offg = off;  // offset + current group's effect
+  u64 accg = ZERO, sd = ZERO;
   float lpa_hi = 0.f, lpa_lo = 0.f, lpb_hi = 0.f, lpb_lo = 0.f;
-  const u64 LOG2E = pk(1.4426950408889634f, 1.4426950408889634f);
-  const u64 NEG1 = pk(-1.f, -1.f);
-  const u64 INVS = pk(p.fixed_inv_scale, p.fixed_inv_scale);
 
   for (int k = 0; k < my_tiles; ++k) {
     const int t = tile0 + k, s = k % XSTAGES;
     const int rows = tile_rows(t);
-    {
-      const int kn = k + XSTAGES - 1;
-      if (tid == 0 && kn < my_tiles && tile_rows(tile0 + kn) == XR) issue(tile0 + kn, kn % XSTAGES);
-    }
     GRaw<PD>& T = raw[s];
     const long long base = (long long)t * XR;
     if (rows == XR) {
       wait_full(s, (k / XSTAGES) & 1);
-    } else {
+    } else {  // ragged last tile of the data
+      __syncthreads();  // every warp has left the tile that used this stage before
       for (int r = tid; r < rows; r += blockDim.x) {
         T.y[r] = p.y[base + r];
         if constexpr (GROUP) T.g[r] = p.gidx[base + r];
@@ -123,7 +131,8 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
     // rows of this tile that belong to the CTA's (group-aligned) range
     const int ra = (int)max(r0 - base, 0LL);
     const int rb = (int)min((long long)rows, r1 - base);
-    u64 lp2 = ZERO;
+    u64 lp2 = ZERO, lpm = ZERO;  // Poisson: lp2 = sum y eta', lpm = sum mu
+    (void)lpm;
 #pragma unroll 2
     for (int r = ra; r < rb; ++r) {
       float xv[PD];
@@ -132,7 +141,6 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
         const float4 v = *reinterpret_cast<const float4*>(&T.x[r * PD + j4]);
         xv[j4] = v.x; xv[j4 + 1] = v.y; xv[j4 + 2] = v.z; xv[j4 + 3] = v.w;
       }
-      u64 eta = off;
       if constexpr (GROUP) {
         const int gi = T.g[r];
         if (gi != curg) {  // warp-uniform
@@ -140,25 +148,34 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
             if (curg >= 0) {
               u64* q = reinterpret_cast<u64*>(p.gbT + (size_t)curg * ldc + c);
               *q = add2(*q, accg);
+              sd = add2(sd, accg);
             }
           }
           curg = gi;
-          bg = *reinterpret_cast<const u64*>(p.bT + (size_t)gi * ldc + c);
+          u64 bg = *reinterpret_cast<const u64*>(p.bT + (size_t)gi * ldc + c);
+          // the next group's lines: a dependent global load per group change would otherwise stall
+          // the warp for a full L2/HBM round trip every ~50 rows
+          if (gi + 1 < p.G) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bT + (size_t)(gi + 1) * ldc + c));
+            if constexpr (GRAD) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.gbT + (size_t)(gi + 1) * ldc + c));
+          }
+          if constexpr (FAM == FAM_POISSON) bg = mul2(bg, LOG2E);
+          offg = add2(off, bg);
           accg = ZERO;
         }
-        eta = add2(eta, bg);
       }
+      u64 eta = offg;
 #pragma unroll
       for (int j = 0; j < PD; ++j) eta = fma2(bc(xv[j]), b[j], eta);
       const float yv = T.y[r];
       u64 d;
       if constexpr (FAM == FAM_POISSON) {
-        const u64 tt = mul2(eta, LOG2E);
         float ta, tb;
-        upk(tt, ta, tb);
+        upk(eta, ta, tb);  // log2(e) * eta
         const u64 mu = pk(ex2f(ta), ex2f(tb));
-        lp2 = add2(lp2, fma2(bc(yv), eta, mul2(mu, NEG1)));  // y*eta - mu
-        d = fma2(mu, NEG1, bc(yv));                          // y - mu
+        lp2 = fma2(bc(yv), eta, lp2);
+        lpm = add2(lpm, mu);
+        d = fma2(mu, NEG1, bc(yv));  // y - mu
       } else if constexpr (FAM == FAM_NORMAL_FIXED) {
         const u64 z = mul2(fma2(eta, NEG1, bc(yv)), INVS);
         lp2 = fma2(mul2(z, pk(-0.5f, -0.5f)), z, lp2);
@@ -172,17 +189,34 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
         d = pk(da, db);
       }
       if constexpr (GRAD) {
-        sd = add2(sd, d);
-        if constexpr (GROUP) accg = add2(accg, d);
+        if constexpr (GROUP) accg = add2(accg, d);  // (sd collects the groups' sums when they close)
+        else sd = add2(sd, d);
 #pragma unroll
         for (int j = 0; j < PD; ++j) g[j] = fma2(bc(xv[j]), d, g[j]);
       }
     }
     float la, lb;
     upk(lp2, la, lb);
+    if constexpr (FAM == FAM_POISSON) {  // ln2 * sum(y eta') - sum mu
+      float ma, mb;
+      upk(lpm, ma, mb);
+      la = fmaf(0.6931471805599453f, la, -ma);
+      lb = fmaf(0.6931471805599453f, lb, -mb);
+    }
     kahan_add(lpa_hi, lpa_lo, la);
     kahan_add(lpb_hi, lpb_lo, lb);
-    __syncthreads();
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(&done[s], 1) == (int)(blockDim.x >> 5) - 1) {  // last warp out refills the stage
+        done[s] = 0;
+        const int kn = k + XSTAGES;
+        if (kn < my_tiles && tile_rows(tile0 + kn) == XR) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(tile0 + kn, s);
+        }
+      }
+    }
   }
 
   if constexpr (GRAD) {
@@ -190,6 +224,7 @@ dgroup_x2_kernel(const __grid_constant__ EvalParams<float> p, int fstride) {
       if (curg >= 0) {
         u64* q = reinterpret_cast<u64*>(p.gbT + (size_t)curg * ldc + c);
         *q = add2(*q, accg);
+        sd = add2(sd, accg);
       }
     }
 #pragma unroll
@@ -215,10 +250,17 @@ bool dgroup_x2_eligible(const lslb_plan* plan) {
 
 LaunchCfg dgroup_x2_cfg(const lslb_plan* plan, int C) {
   LaunchCfg k;
-  k.TC = 256;
-  k.Cpad = (C + k.TC - 1) / k.TC * k.TC;
-  k.ntiles = k.Cpad / k.TC;
-  long long want = ((long long)plan->sm_count * 4 + k.ntiles - 1) / k.ntiles;
+  // chains spread evenly over the chain tiles in whole warps (64 chains), at most 16 warps per CTA;
+  // with few chains several CTAs share an SM so that it still holds ~16 warps
+  k.ntiles = (C + 1023) / 1024;
+  const int per_tile = (C + k.ntiles - 1) / k.ntiles;
+  const int U = (per_tile + 63) / 64;
+  k.TC = 64 * U;
+  k.Cpad = k.ntiles * k.TC;
+  int cps = 16 / U;
+  if (cps < 1) cps = 1;
+  if (cps > 5) cps = 5;  // shared memory: 30-37 KB of row stages per CTA
+  long long want = ((long long)plan->sm_count * cps) / k.ntiles;
   if (want < 1) want = 1;
   int F = plan->nchunks;
   k.fstride = (int)((F + want - 1) / want);
@@ -230,7 +272,7 @@ LaunchCfg dgroup_x2_cfg(const lslb_plan* plan, int C) {
 template <int PD, int FAM>
 static int dg_go(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k, bool g,
                  cudaStream_t st) {
-  dim3 grid(k.ntiles, k.nchunks), block(128);
+  dim3 grid(k.ntiles, k.nchunks), block(k.TC / 2);
   const bool grp = plan->grp >= 0;
   if (grp) {
     if (g) dgroup_x2_kernel<PD, FAM, true, true><<<grid, block, 0, st>>>(ep, k.fstride);
