@@ -56,6 +56,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   __shared__ __align__(128) XRaw<NS> raw[X2S];
   __shared__ __align__(8) u64 full[X2S];
   __shared__ int done[X2S];  // warps that have finished with the tile in stage s
+  __shared__ __align__(16) float tws[X2S][NS][4];  // the tile's weight-column sums (plan constant)
 
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
@@ -90,7 +91,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   };
   auto issue = [&](int t, int s) {
     const long long r0 = (long long)t * XR;
-    constexpr unsigned bytes = XR * 4 + NS * (XR * 16 + XR * 4);
+    constexpr unsigned bytes = XR * 4 + NS * (XR * 16 + XR * 4 + 16);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(&full[s])),
                  "r"(bytes)
                  : "memory");
@@ -99,6 +100,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     for (int m = 0; m < NS; ++m) {
       bulk(raw[s].w[m], p.sp[m].w + 4 * r0, XR * 16, &full[s]);
       bulk(raw[s].start[m], p.sp[m].start + r0, XR * 4, &full[s]);
+      bulk(tws[s][m], p.sp[m].tw + 4 * (long long)t, 16, &full[s]);
     }
   };
   auto wait_full = [&](int s, unsigned parity) {
@@ -304,7 +306,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           float ta, tb;
           upk(eta1[i], ta, tb);  // already -log2(e) * eta1
           inv_s = pk(ex2f(ta), ex2f(tb));  // exp(-eta1)
-          se1 = add2(se1, eta1[i]);
+          if constexpr (!FAST) se1 = add2(se1, eta1[i]);  // FAST: closed form per tile, below
         } else {
           inv_s = INVS_FIXED;
         }
@@ -402,6 +404,20 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
             compute_block(wa, ya, N4{}, TFast{});
             if (r + 2 * NRB < XR) load_block(wa, ya, r + 2 * NRB, N4{});
             compute_block(wbuf, yb, N4{}, TFast{});
+          }
+          if constexpr (FAM == FAM_NORMAL_LS) {
+            // sum over the tile's rows of predictor 1 in closed form: every row is
+            // e1i + sum_{u != 1} w_u (b_u - b_1), and the column sums of w are a plan constant
+            se1 = mul2(e1i, pk((float)XR, (float)XR));
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+              if ((PM >> m) & 1) {
+                const float4 tw = *reinterpret_cast<const float4*>(tws[s][m]);
+                se1 = fma2(bc(tw.x), wb[m][0], se1);
+                se1 = fma2(bc(tw.z), wb[m][2], se1);
+                se1 = fma2(bc(tw.w), wb[m][3], se1);
+              }
+            }
           }
         } else {
 #pragma unroll 1

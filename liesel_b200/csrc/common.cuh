@@ -48,6 +48,7 @@ struct SplP {
   int k;
   int pred;
   int pad;
+  const float* tw;   // banded_x2 only: per 128-row tile the column sums of w, [ntiles][4] (plan-owned)
 };
 template <typename T>
 struct DnsP {
@@ -223,6 +224,7 @@ struct lslb_plan {
   bool unit_rows;    // every spline row's four weights sum to one (x inside the knot range)
   float* d_XT;       // tensor-core path (or NULL): plan-owned hi part of the transposed dense block [p x n_pad]
   float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
+  float* d_tw[LSLB_MAX_SPL];   // float32 banded plans: per 128-row tile the column sums of each smooth's weights
   long long n_pad;
   int variant;
   const char* variant_name;

@@ -591,7 +591,7 @@ void fill_eval_params(const lslb_plan* plan, EvalParams<T>& ep, int C, int Cpad)
   for (int m = 0; m < plan->ns; ++m) {
     const lslb_block_desc& d = plan->blk[plan->sp[m]];
     ep.sp[m] = {reinterpret_cast<const T*>(d.data), d.index, plan->soff[plan->sp[m]], d.ncoef,
-                d.predictor, 0};
+                d.predictor, 0, plan->d_tw[m]};
   }
   for (int m = 0; m < plan->nd; ++m) {
     const lslb_block_desc& d = plan->blk[plan->dn[m]];

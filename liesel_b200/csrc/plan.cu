@@ -62,6 +62,22 @@ __global__ void unit_rows_kernel(const T* __restrict__ w, long long n, double* o
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// per 128-row tile the sums of the four weight columns of one spline block (one block per tile)
+__global__ void tile_weight_sums_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * 128;
+  const int u = threadIdx.x & 3, q = threadIdx.x >> 2;  // 32 row slots x 4 columns
+  double acc = 0.0;
+  for (int r = q; r < 128 && r0 + r < n; r += 32) acc += (double)w[4 * (r0 + r) + u];
+  __shared__ double sh[128];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int j = 0; j < 32; ++j) t += sh[4 * j + threadIdx.x];  // fixed order
+    out[4 * (long long)blockIdx.x + threadIdx.x] = (float)t;
+  }
+}
+
 // sum_i lgamma(y_i + 1) in double, one block, fixed order (deterministic)
 template <typename T>
 __global__ void lgamma_sum_kernel(const T* __restrict__ y, long long n, double* out) {
@@ -274,6 +290,20 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   }
   dense_tc_prepare(p);
   if (p->d_XT) p->variant_name = "dense_tcgen05_tf32x3";
+  if (p->variant == VAR_BANDED && desc->dtype == LSLB_F32 && n > 0) {
+    const long long ntiles = (n + 127) / 128;
+    for (int m = 0; m < p->ns && e == cudaSuccess; ++m) {
+      e = cudaMalloc(&p->d_tw[m], sizeof(float) * 4 * ntiles);
+      if (e == cudaSuccess)
+        tile_weight_sums_kernel<<<(unsigned)ntiles, 128>>>((const float*)p->blk[p->sp[m]].data, n, p->d_tw[m]);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "tile weight sums");
+      lslb_plan_destroy(p);
+      return LSLB_ERR_CUDA;
+    }
+  }
   *out = p;
   return LSLB_OK;
 }
@@ -281,6 +311,8 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
 extern "C" void lslb_plan_destroy(lslb_plan* p) {
   if (!p) return;
   if (p->d_chunk_start) cudaFree(p->d_chunk_start);
+  for (int m = 0; m < LSLB_MAX_SPL; ++m)
+    if (p->d_tw[m]) cudaFree(p->d_tw[m]);
   lslb::dense_tc_release(p);
   delete p;
 }
