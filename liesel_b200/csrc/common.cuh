@@ -226,6 +226,7 @@ struct lslb_plan {
   float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
   float* d_tw[LSLB_MAX_SPL];   // float32 banded plans: per 128-row tile the column sums of each smooth's weights
   long long n_pad;
+  bool tc_two_pass;  // tensor-core path: two TF32 passes per product are enough for this data (plan-time check)
   int variant;
   const char* variant_name;
 };
@@ -257,6 +258,7 @@ struct BandedCfg {
 };
 struct TcCfg {
   int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;
+  int two_pass;  // drop the products with a lo factor of the large operands (see dense_tc_prepare)
 };
 int dense_tc_prepare(lslb_plan* plan);                 // dense_tc.cu (called by lslb_plan_create)
 void dense_tc_release(lslb_plan* plan);

@@ -108,15 +108,23 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// hi part of the operand split: x rounded to nearest TF32 (10-bit mantissa, low 13 bits zero);
+// lo = x - hi is exact in fp32. Round-to-nearest (not truncation) makes lo zero-mean, which the
+// two-pass mode relies on when it drops a product with a lo factor.
+__device__ __forceinline__ float tf32_rn(float x) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 // element-wise hi/lo split of `count` floats: hi stays in `h`, lo goes to `l`
 __device__ __forceinline__ void split_tile(float* h, float* l, int count, int t, int nthreads) {
   for (int i = 4 * t; i < count; i += 4 * nthreads) {
     float4 v = *reinterpret_cast<float4*>(h + i);
     float4 hi, lo;
-    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
-    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
-    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
-    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+    hi.x = tf32_rn(v.x); lo.x = v.x - hi.x;
+    hi.y = tf32_rn(v.y); lo.y = v.y - hi.y;
+    hi.z = tf32_rn(v.z); lo.z = v.z - hi.z;
+    hi.w = tf32_rn(v.w); lo.w = v.w - hi.w;
     *reinterpret_cast<float4*>(h + i) = hi;
     *reinterpret_cast<float4*>(l + i) = lo;
   }
@@ -154,7 +162,8 @@ __global__ void __launch_bounds__(64 + 128 * K1_GROUPS, 1)
 dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ CUtensorMap mapPl,
             const __grid_constant__ CUtensorMap mapXh, const __grid_constant__ CUtensorMap mapXl,
             const __grid_constant__ CUtensorMap mapRT, const float* __restrict__ y, long long n, long long n_pad, int p, int tiles_per_cta, int ntiles,
-            float fixed_inv_scale, float* __restrict__ RT, float* __restrict__ partial, int Psmall, int Cpad) {
+            float fixed_inv_scale, float* __restrict__ RT, float* __restrict__ partial, int Psmall, int Cpad,
+            int two_pass) {
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
   K1Stage* st = reinterpret_cast<K1Stage*>(smraw);
@@ -197,11 +206,11 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
         const int row0 = (tile0 + t) * NR1;
         for (int kc = 0; kc < nk; ++kc) {
           bar_wait(&empty[q.s], q.ph ^ 1);
-          bar_expect(&full[q.s], 2 * (MT + NR1) * KC * 4);
+          bar_expect(&full[q.s], (2 * MT + ((two_pass & 1) ? 1 : 2) * NR1) * KC * 4);
           tma2d(st[q.s].ah, &mapPh, kc * KC, chain0, &full[q.s]);
           tma2d(st[q.s].al, &mapPl, kc * KC, chain0, &full[q.s]);
           tma2d(st[q.s].bh, &mapXh, kc * KC, row0, &full[q.s]);
-          tma2d(st[q.s].bl, &mapXl, kc * KC, row0, &full[q.s]);
+          if (!(two_pass & 1)) tma2d(st[q.s].bl, &mapXl, kc * KC, row0, &full[q.s]);
           q.next();
         }
       }
@@ -226,7 +235,7 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
             const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
             mma_tf32(d, ah, bh, idesc, (kc | k8) != 0);
             mma_tf32(d, al, bh, idesc, 1);
-            mma_tf32(d, ah, bl, idesc, 1);
+            if (!(two_pass & 1)) mma_tf32(d, ah, bl, idesc, 1);  // two-pass: hi(beta) . lo(x) dropped (zero-mean)
           }
           mma_commit(&empty[q.s]);
           q.next();
@@ -266,7 +275,8 @@ dense_tc_k1(const __grid_constant__ CUtensorMap mapPh, const __grid_constant__ C
           lik_row<float, FAM, false>(__ldg(y + (valid ? row : 0)), __uint_as_float(r[j]), 0.f, fixed_inv_scale,
                                      ll, d0, d1, w0, w1);
           lp_tile += valid ? ll : 0.f;
-          dres[j] = valid ? d0 : 0.f;
+          // two-pass: K2 takes the residual as ONE TF32 operand, so it is rounded (to nearest) here
+          dres[j] = valid ? ((two_pass & 2) ? tf32_rn(d0) : d0) : 0.f;
         }
         if constexpr (GRAD) {
           // residual tile -> swizzled staging -> one TMA store (full 128-byte lines of R^T per chain)
@@ -343,7 +353,7 @@ template <int NP>
 __global__ void __launch_bounds__(192, 1)
 dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ CUtensorMap mapXTl,
             const __grid_constant__ CUtensorMap mapRT, int p, int kchunks_per_cta, int nkchunks, int soff,
-            float* __restrict__ partial, int Psmall, int Cpad) {
+            float* __restrict__ partial, int Psmall, int Cpad, int two_pass) {
   extern __shared__ unsigned char smraw_[];
   unsigned char* smraw = smraw_ + ((1024u - (sm(smraw_) & 1023u)) & 1023u);
   K2Stage<NP>* st = reinterpret_cast<K2Stage<NP>*>(smraw);
@@ -399,7 +409,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ 
           const u64t ah = desc_k_sw128(st[q.s].ah, kb), al = desc_k_sw128(st[q.s].al, kb);
           const u64t bh = desc_k_sw128(st[q.s].bh, kb), bl = desc_k_sw128(st[q.s].bl, kb);
           mma_tf32(tmem_base, ah, bh, idesc, (kc | k8) != 0);
-          mma_tf32(tmem_base, al, bh, idesc, 1);
+          if (!(two_pass & 2)) mma_tf32(tmem_base, al, bh, idesc, 1);  // two-pass: the residual is already TF32
           mma_tf32(tmem_base, ah, bl, idesc, 1);
         }
         mma_commit(&empty[q.s]);
@@ -414,7 +424,7 @@ dense_tc_k2(const __grid_constant__ CUtensorMap mapXTh, const __grid_constant__ 
     PipeT<STAGES> q;
     for (int kc = 0; kc < my_k; ++kc) {
       bar_wait(&full_raw[q.s], q.ph);
-      split_tile(st[q.s].ah, st[q.s].al, NC2 * KC, t128, 128);
+      if (!(two_pass & 2)) split_tile(st[q.s].ah, st[q.s].al, NC2 * KC, t128, 128);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bar_arrive(&full_split[q.s]);
       q.next();
@@ -454,7 +464,7 @@ __global__ void split_matrix_kernel(const float* __restrict__ src, long long row
   const long long r = i / cols;
   const int c = (int)(i % cols);
   const float v = src[r * ld_src + c];
-  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  const float h = tf32_rn(v);
   hi[r * ld_dst + c] = h;
   lo[r * ld_dst + c] = v - h;
 }
@@ -466,7 +476,7 @@ __global__ void split_params_kernel(const float* __restrict__ params, int C, int
   if (i >= Cpad * p) return;
   const int c = i / p, j = i % p;
   const float v = c < C ? params[(size_t)c * P + j] : 0.f;
-  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  const float h = tf32_rn(v);
   ph[i] = h;
   pl[i] = v - h;
 }
@@ -491,12 +501,26 @@ __global__ void transpose_block_split_kernel(const float* __restrict__ X, long l
     const long long r = r0 + threadIdx.x;
     if (c < p && r < n_pad) {
       const float v = tile[threadIdx.x][k];
-      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      const float h = tf32_rn(v);
       const size_t d = ((size_t)(r / KC) * p + c) * KC + (size_t)(r % KC);
       hi[d] = h;
       lo[d] = v - h;
     }
   }
+}
+// per column of a row-major [rows x cols] matrix: sum and sum of squares (setup time)
+__global__ void col_stats_kernel(const float* __restrict__ m, long long rows, int cols, double* __restrict__ out) {
+  const int c = threadIdx.x % cols, sub = threadIdx.x / cols, nsub = blockDim.x / cols;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long r = r0 + sub; r < r1; r += nsub) {
+    const double v = (double)m[r * cols + c];
+    s1 += v;
+    s2 += v * v;
+  }
+  atomicAdd(&out[2 * c], s1);
+  atomicAdd(&out[2 * c + 1], s2);
 }
 }  // namespace tc
 
@@ -553,6 +577,29 @@ int dense_tc_prepare(lslb_plan* plan) {
     return LSLB_OK;
   }
   plan->n_pad = n_pad;
+  // Two-pass mode: with many rows, hi(beta).lo(x) in K1 and lo(r).hi(x) in K2 are sums of
+  // zero-mean rounding residues and stay far below the fp32 tolerance — PROVIDED no column's lo part
+  // has a systematic component (a constant column of a value that TF32 cannot represent would shift
+  // eta by the same amount in every row). Checked here per column: |mean| within 6 standard errors.
+  plan->tc_two_pass = false;
+  if (n >= (1 << 19)) {
+    double* d_st = nullptr;
+    if (cudaMalloc(&d_st, sizeof(double) * 2 * p) == cudaSuccess) {
+      cudaMemset(d_st, 0, sizeof(double) * 2 * p);
+      tc::col_stats_kernel<<<1024, 256>>>(plan->d_Xl, n, p, d_st);
+      double h[512];
+      if (cudaMemcpy(h, d_st, sizeof(double) * 2 * p, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        bool ok = true;
+        for (int j = 0; j < p; ++j) {
+          const double mean = h[2 * j] / (double)n, ms = h[2 * j + 1] / (double)n;
+          if (fabs(mean) > 6.0 * sqrt(ms / (double)n) + 1e-300) ok = false;
+        }
+        plan->tc_two_pass = ok;
+      }
+      cudaFree(d_st);
+    }
+    cudaGetLastError();
+  }
   return LSLB_OK;
 }
 
@@ -569,8 +616,21 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
   if (want < 1) want = 1;
   if (want > k.ntiles_rows) want = k.ntiles_rows;
   k.tiles_per_cta = (int)((k.ntiles_rows + want - 1) / want);
+  // K2 accumulates a CTA's whole row range in ONE fp32 TMEM accumulator, and the tensor core adds
+  // into it with truncation: the bias grows with the number of MMAs in the chain (measured at
+  // n = 6e5, 33k rows per CTA: a constant column used 2.1x the gradient tolerance). Shorter chains
+  // (more split-K chunks, summed in double by finalize) bound it.
+  int rows_cap = 2048;  // 0.44-0.58 of the gradient tolerance at n = 6e5 (4096: 0.63-0.91, 8192: 0.99-1.8)
+  if (const char* e = getenv("LSLB_TC_ROWS_PER_CTA")) rows_cap = atoi(e) >= tc::NR1 ? atoi(e) : rows_cap;  // tuning knob
+  if (k.tiles_per_cta > rows_cap / tc::NR1) k.tiles_per_cta = rows_cap / tc::NR1;
   k.nchunks = (k.ntiles_rows + k.tiles_per_cta - 1) / k.tiles_per_cta;
   k.kchunks_per_cta = k.tiles_per_cta * (tc::NR1 / tc::KC);
+  // bit 0: K1 (eta) in two passes; bit 1: K2 (gradient) in two passes. Default: K1 only — measured
+  // at n = 6e5 the worst gradient entry uses ~0.4 of the tolerance with K1 alone and 1.3 with both
+  // (the rounded residual's lo part is the larger of the two dropped terms).
+  k.two_pass = plan->tc_two_pass ? 1 : 0;
+  if (const char* e = getenv("LSLB_TC_PASSES"))  // A/B runs: 3 = three passes everywhere, 2 = two passes in K1 and K2
+    k.two_pass = atoi(e) == 2 ? 3 : (atoi(e) == 3 ? 0 : k.two_pass);
   return k;
 }
 
@@ -606,12 +666,12 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
     auto kern = tc::dense_tc_k1<FAM, true>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
-                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
   } else {
     auto kern = tc::dense_tc_k1<FAM, false>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
-                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad);
+                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
   }
   LSLB_LAUNCH_CHECK();
   if (!g) return LSLB_OK;
@@ -625,13 +685,13 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
     auto kern = tc::dense_tc_k2<256>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     kern<<<grid2, 192, smem2, st>>>(mXTh, mXTl, mRTld, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall,
-                                    k.Cpad);
+                                    k.Cpad, k.two_pass);
   } else {
     const size_t smem2 = tc::STAGES * sizeof(tc::K2Stage<128>) + 1024;
     auto kern = tc::dense_tc_k2<128>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     kern<<<grid2, 192, smem2, st>>>(mXTh, mXTl, mRTld, p, k.kchunks_per_cta, k.nkchunks, soff, partial, plan->Psmall,
-                                    k.Cpad);
+                                    k.Cpad, k.two_pass);
   }
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;

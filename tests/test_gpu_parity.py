@@ -672,6 +672,75 @@ def test_dense_tcgen05_logistic(lb, p, n, C):
     np.testing.assert_allclose(lp_s.cpu().numpy(), logp.cpu().numpy()[:64], rtol=2e-6)
 
 
+def test_dense_tcgen05_two_pass_large_n(lb):
+    """
+    From 2^19 rows on (and when no column's TF32 rounding residue has a systematic component) the
+    tensor-core path drops the two products with a lo factor of the large operands. Same tolerance
+    as everywhere (rtol 1e-5 + 16 ulps of the term scale); reported: how much of it is used.
+    """
+    spec, centre = synth.s4_logistic(n=600_000, p=128, dtype=np.float32)
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_tcgen05_tf32x3"
+    C = 256
+    th, aux = synth.evaluation_points(spec, centre, C)
+    sel = [0, 131, C - 1]
+    logp, grad = plan.logp_grad(dev(th, plan), None)
+    logp_v, _ = plan.logp_grad(dev(th, plan), None, want_grad=False)
+    torch.cuda.synchronize()
+    prep = sam.Prepared(spec)
+    ref_lp = sam.log_prob(spec, th[sel], prep=prep)
+    ref_g = sam.grad(spec, th[sel], prep=prep)
+    sc_g = sam.grad_scale(spec, th[sel], prep=prep)
+    sc_lp = sam.log_prob_scale(spec, th[sel], prep=prep)
+    lp = logp.cpu().numpy()[sel]
+    np.testing.assert_allclose(logp_v.cpu().numpy()[sel], lp, rtol=1e-6)
+    lerr = np.abs(lp - ref_lp) / (1e-5 * np.abs(ref_lp) + ULPS * 2.0**-24 * sc_lp)
+    gerr = np.abs(grad.cpu().numpy()[sel] - ref_g) / (1e-5 * np.abs(ref_g) + ULPS * 2.0**-24 * sc_g)
+    print(f"two-pass tolerance use: logp {lerr.max():.3f}, grad {gerr.max():.3f}")
+    assert lerr.max() <= 1.0 and gerr.max() <= 1.0, (float(lerr.max()), float(gerr.max()))
+    # a constant column that TF32 cannot represent makes the rounding residue systematic: such data
+    # must stay on three passes (checked through the result: it still meets the tolerance)
+    import dataclasses
+
+    X2 = spec.blocks[0].X.copy()
+    X2[:, 5] = np.float32(0.1)
+    spec2 = dataclasses.replace(spec, blocks=[dataclasses.replace(spec.blocks[0], X=X2)])
+    plan2 = lb.Plan(spec2)
+    lp2, g2 = plan2.logp_grad(dev(th, plan2), None)
+    torch.cuda.synchronize()
+    r_lp = sam.log_prob(spec2, th[sel])
+    r_g = sam.grad(spec2, th[sel])
+    s_g = sam.grad_scale(spec2, th[sel])
+    s_lp = sam.log_prob_scale(spec2, th[sel])
+    assert np.all(np.abs(lp2.cpu().numpy()[sel] - r_lp) <= 1e-5 * np.abs(r_lp) + ULPS * 2.0**-24 * s_lp)
+    g2err = np.abs(g2.cpu().numpy()[sel] - r_g) / (1e-5 * np.abs(r_g) + ULPS * 2.0**-24 * s_g)
+    print(f"constant-column data: grad tolerance use {g2err.max():.3f} at {np.unravel_index(g2err.argmax(), g2err.shape)}")
+    assert g2err.max() <= 1.0, float(g2err.max())
+
+
+def test_full_size_s4_shard_against_oracle(lb):
+    """One S4 shard at BASELINE size (1.25e6 rows x 256, 1024 chains) against the fp64 oracle on three
+    chains: the tensor-core path's accumulation error grows with the rows a CTA sums, so small-n parity
+    says nothing about this size."""
+    spec, centre = synth.s4_logistic(n=10_000_000, p=256, world_size=8, rank=3)
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_tcgen05_tf32x3" and spec.n == 1_250_000
+    C = 1024
+    th, aux = synth.evaluation_points(spec, centre, C)
+    sel = [0, 517, C - 1]
+    logp, grad = plan.logp_grad(dev(th, plan), None)
+    torch.cuda.synchronize()
+    prep = sam.Prepared(spec)
+    ref_lp = sam.log_prob(spec, th[sel], prep=prep)
+    ref_g = sam.grad(spec, th[sel], prep=prep)
+    sc_g = sam.grad_scale(spec, th[sel], prep=prep)
+    sc_lp = sam.log_prob_scale(spec, th[sel], prep=prep)
+    lerr = np.abs(logp.cpu().numpy()[sel] - ref_lp) / (1e-5 * np.abs(ref_lp) + ULPS * 2.0**-24 * sc_lp)
+    gerr = np.abs(grad.cpu().numpy()[sel] - ref_g) / (1e-5 * np.abs(ref_g) + ULPS * 2.0**-24 * sc_g)
+    print(f"S4 shard tolerance use: logp {lerr.max():.3f}, grad {gerr.max():.3f}")
+    assert lerr.max() <= 1.0 and gerr.max() <= 1.0, (float(lerr.max()), float(gerr.max()))
+
+
 def test_device_diagnostics_on_gpu(lb):
     """Bulk-ESS and split-R-hat computed on the GPU that stores the draws equal the host versions."""
     from liesel_b200 import diagnostics
