@@ -623,6 +623,23 @@ def test_full_size_h_properties(lb):
     np.testing.assert_allclose(acc_g.cpu().numpy(), g[:256].double().cpu().numpy(), rtol=1e-4, atol=1e-5 * gmax)
 
 
+def test_full_size_h_and_s5_against_oracle(lb):
+    """BASELINE sizes against the fp64 oracle itself on three chains each (the oracle needs seconds
+    per chain at these sizes), same tolerance as the small cases: errors that grow with the number of
+    rows a CTA sums do not show at n = 5e4."""
+    spec, centre = synth.s3_gamlss(n=1_000_000)
+    plan = lb.Plan(spec)
+    assert plan.variant == "banded_tma_runlength"
+    th, aux = synth.evaluation_points(spec, centre, 1024, tau2="loguniform")
+    check_logp_grad(spec, plan, th, aux, chains=[0, 411, 1023])
+    del plan
+    spec, centre = synth.s5_poisson_ri()
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_group_x2_tma"
+    th, aux = synth.evaluation_points(spec, centre, 1024)
+    check_logp_grad(spec, plan, th, aux, chains=[0, 1023])
+
+
 def test_full_size_s5_group_sum_properties(lb):
     """S5 at full size: the random-intercept gradient is a segment sum — summing it over groups must
     equal the fixed-intercept column's gradient divided by its constant (0.3), prior terms removed."""
