@@ -39,6 +39,19 @@ class B200Interface:
             b.name + "_beta": slice(b.param_offset, b.param_offset + b.ncoef) for b in spec.blocks
         }
 
+    @classmethod
+    def from_model(cls, model, device=None, **match_kw) -> "B200Interface":
+        """
+        From a DistReg-shaped ``liesel.model.Model`` (``from_liesel.spec_from_model`` pattern-matches
+        the graph; raises ``UnsupportedModelError`` for anything else, in which case the caller keeps
+        ``gs.LieselInterface(model)``). The data is read out of the model once; afterwards only the
+        parameter-only state travels through the engine.
+        """
+        from .from_liesel import spec_from_model
+
+        spec = spec_from_model(model, **match_kw)
+        return cls(Plan(spec, device=device) if device is not None else Plan(spec))
+
     # -- ModelInterface protocol (types.py:72-102) ------------------------------------
     def extract_position(self, position_keys: Sequence[str], model_state: ModelState) -> Position:
         """Same contract as ``DictInterface.extract_position`` (``interface.py:75-88``)."""
