@@ -138,6 +138,22 @@ def test_ragged_chain_counts(lb, C):
     check_logp_grad(spec, plan, th, aux)
 
 
+@pytest.mark.parametrize("C", [129, 192, 320, 576, 704, 1088])
+def test_chain_counts_with_ring_wraparound(lb, C):
+    """Chain counts that give 3..16 warps per CTA and 1..5 CTAs per SM, at a row count where every CTA
+    walks more tiles than the TMA ring has stages (the small cases never refill a stage)."""
+    spec, centre = synth.s3_gamlss(n=150_000 + 37)
+    plan = lb.Plan(spec)
+    assert plan.variant == "banded_tma_runlength"
+    th, aux = synth.evaluation_points(spec, centre, C, tau2="loguniform")
+    check_logp_grad(spec, plan, th, aux, chains=[0, 63, 64, C - 1])
+    spec, centre = synth.s5_poisson_ri(n=150_000, G=2900, balanced=False)
+    plan = lb.Plan(spec)
+    assert plan.variant == "dense_group_x2_tma"
+    th, aux = synth.evaluation_points(spec, centre, C)
+    check_logp_grad(spec, plan, th, aux, chains=[0, C - 1])
+
+
 def test_unsorted_rows_same_result(lb):
     """Row order is free: the span-sorted plan and the plan in data order agree."""
     spec, centre = make("s2", np.float32)
