@@ -30,8 +30,12 @@ ModelState = dict
 
 
 class B200Interface:
-    def __init__(self, plan: Plan):
+    def __init__(self, plan: Plan, shard=None):
+        """``shard``: a ``dist.PeerGroup`` / ``dist.NcclComm`` when ``plan`` holds ONE RANK'S ROWS of
+        the data (``ModelSpec.rows``): every evaluation is then summed over the ranks inside the C
+        call, and each rank's interface returns the log-posterior of the full data."""
         self.plan = plan
+        self.shard = shard
         spec = plan.spec
         self._pos_keys = spec.position_keys()
         self._aux_keys = spec.aux_keys()
@@ -67,13 +71,13 @@ class B200Interface:
     def log_prob(self, model_state: ModelState) -> torch.Tensor:
         """Unnormalised log-posterior per chain, ``[C]`` (``interface.py:304-313``)."""
         params, aux = self.pack(model_state)
-        logp, _ = self.plan.logp_grad(params, aux, want_grad=False)
+        logp, _ = self.plan.logp_grad(params, aux, want_grad=False, shard=self.shard)
         return logp
 
     # -- what jax.value_and_grad(log_prob_fn) yields in NUTS/HMC (nuts.py:193-194) ----
     def log_prob_and_grad(self, model_state: ModelState, position_keys: Sequence[str] | None = None):
         params, aux = self.pack(model_state)
-        logp, grad = self.plan.logp_grad(params, aux, want_grad=True)
+        logp, grad = self.plan.logp_grad(params, aux, want_grad=True, shard=self.shard)
         keys = self._pos_keys if position_keys is None else list(position_keys)
         bad = [k for k in keys if k not in self._slices]
         if bad:
@@ -86,14 +90,14 @@ class B200Interface:
 
         def fn(model_state: ModelState) -> torch.Tensor:
             params, aux = self.pack(model_state)
-            _, _, chol = self.plan.iwls(block, params, aux, want_chol=True)
+            _, _, chol = self.plan.iwls(block, params, aux, want_chol=True, shard=self.shard)
             return chol
 
         return fn
 
     def score_and_info(self, position_key: str, model_state: ModelState, want_chol: bool = True):
         params, aux = self.pack(model_state)
-        return self.plan.iwls(self._block_of(position_key), params, aux, want_chol=want_chol)
+        return self.plan.iwls(self._block_of(position_key), params, aux, want_chol=want_chol, shard=self.shard)
 
     # -- state helpers -----------------------------------------------------------------
     def initial_state(self, num_chains: int, position: dict | None = None) -> ModelState:

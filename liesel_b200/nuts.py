@@ -331,7 +331,6 @@ class BatchedNUTS:
         self._graph_ready = True  # the first subtree ran eagerly (lazy one-time initialisation done)
         if idx is None:
             ck_r.copy_(st["ck_r"]); ck_s.copy_(st["ck_s"])
-            res = st
             cl = lambda k: st[k].clone()
         else:
             flush()  # (checkpoints are scratch of ONE subtree: nothing to hand back)

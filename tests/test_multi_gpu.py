@@ -45,6 +45,13 @@ def test_sharded_entry_points_world1():
         s, i, c = plan.iwls("loc_np0", t, ax, shard=sh)
         assert torch.equal(s, s0) and torch.equal(i, i0) and torch.equal(c, c0)
     assert not peer.timed_out()
+    # the reference-facing interface takes the same transport objects
+    from liesel_b200.interface import B200Interface
+
+    iface = B200Interface(plan, shard=peer)
+    state = iface.unpack(t, ax)
+    assert torch.equal(iface.log_prob_and_grad(state)[0], lp0)
+    assert torch.equal(iface.chol_info_fn("loc_np0_beta")(state), c0)
     # a result larger than the exchange buffer is refused with a status code, not a crash
     from liesel_b200 import _lib
 
