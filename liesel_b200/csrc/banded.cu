@@ -319,21 +319,20 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
     k.ntiles_chain = (C + 1023) / 1024;
     const int per_tile = (C + k.ntiles_chain - 1) / k.ntiles_chain;
     k.tc_eff = (per_tile + 63) / 64 * 64;
-    if (const char* e = getenv("LSLB_BANDED_TCEFF"))  // tuning knob: chains per CTA (multiple of 64)
-      if (atoi(e) >= 64 && atoi(e) <= 1024 && atoi(e) % 64 == 0) {
-        k.tc_eff = atoi(e);
-        k.ntiles_chain = (C + k.tc_eff - 1) / k.tc_eff;
-      }
     k.Cpad = k.ntiles_chain * k.tc_eff;
   }
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
   int ctas_per_sm = x2 ? 16 / (k.tc_eff / 64) : 6;  // x2: at most 16 resident warps per SM (registers)
   if (ctas_per_sm > 5) ctas_per_sm = 5;             // shared memory: 34 KB of row stages per CTA
-  if (const char* e = getenv("LSLB_BANDED_CTAS_PER_SM")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;  // tuning knob
+  static const int knob_ctas = [] {  // tuning knob, read once
+    const char* e = getenv("LSLB_BANDED_CTAS_PER_SM");
+    return e ? atoi(e) : 0;
+  }();
+  if (knob_ctas > 0) ctas_per_sm = knob_ctas;
   long long want = ((long long)plan->sm_count * ctas_per_sm + k.ntiles_chain - 1) / k.ntiles_chain;
-  if (const char* e = getenv("LSLB_BANDED_WANT_FLOOR"))  // tuning knob: never exceed one resident wave
-    if (atoi(e) > 0) want = ((long long)plan->sm_count * ctas_per_sm) / k.ntiles_chain;
+  // x2 CTAs hold the SM's whole register file: one CTA too many would run as a second wave
+  if (x2) want = ((long long)plan->sm_count * ctas_per_sm) / k.ntiles_chain;
   if (want < 1) want = 1;
   if (want > k.ntiles_total) want = k.ntiles_total;
   k.tiles_per_cta = (int)((k.ntiles_total + want - 1) / want);

@@ -621,7 +621,15 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
   // n = 6e5, 33k rows per CTA: a constant column used 2.1x the gradient tolerance). Shorter chains
   // (more split-K chunks, summed in double by finalize) bound it.
   int rows_cap = 2048;  // 0.44-0.58 of the gradient tolerance at n = 6e5 (4096: 0.63-0.91, 8192: 0.99-1.8)
-  if (const char* e = getenv("LSLB_TC_ROWS_PER_CTA")) rows_cap = atoi(e) >= tc::NR1 ? atoi(e) : rows_cap;  // tuning knob
+  static const int knob_rows = [] {  // tuning knobs of this function, read once
+    const char* e = getenv("LSLB_TC_ROWS_PER_CTA");
+    return e ? atoi(e) : 0;
+  }();
+  static const int knob_passes = [] {
+    const char* e = getenv("LSLB_TC_PASSES");
+    return e ? atoi(e) : 0;
+  }();
+  if (knob_rows >= tc::NR1) rows_cap = knob_rows;
   if (k.tiles_per_cta > rows_cap / tc::NR1) k.tiles_per_cta = rows_cap / tc::NR1;
   k.nchunks = (k.ntiles_rows + k.tiles_per_cta - 1) / k.tiles_per_cta;
   k.kchunks_per_cta = k.tiles_per_cta * (tc::NR1 / tc::KC);
@@ -629,8 +637,8 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
   // at n = 6e5 the worst gradient entry uses ~0.4 of the tolerance with K1 alone and 1.3 with both
   // (the rounded residual's lo part is the larger of the two dropped terms).
   k.two_pass = plan->tc_two_pass ? 1 : 0;
-  if (const char* e = getenv("LSLB_TC_PASSES"))  // A/B runs: 3 = three passes everywhere, 2 = two passes in K1 and K2
-    k.two_pass = atoi(e) == 2 ? 3 : (atoi(e) == 3 ? 0 : k.two_pass);
+  // A/B runs: 3 = three passes everywhere, 2 = two passes in K1 and K2
+  k.two_pass = knob_passes == 2 ? 3 : (knob_passes == 3 ? 0 : k.two_pass);
   return k;
 }
 

@@ -138,7 +138,7 @@ def test_ragged_chain_counts(lb, C):
     check_logp_grad(spec, plan, th, aux)
 
 
-@pytest.mark.parametrize("C", [129, 192, 320, 576, 704, 1088])
+@pytest.mark.parametrize("C", [129, 192, 320, 576, 704, 1088, 2500])
 def test_chain_counts_with_ring_wraparound(lb, C):
     """Chain counts that give 3..16 warps per CTA and 1..5 CTAs per SM, at a row count where every CTA
     walks more tiles than the TMA ring has stages (the small cases never refill a stage)."""
