@@ -154,6 +154,32 @@ def test_chain_counts_with_ring_wraparound(lb, C):
     check_logp_grad(spec, plan, th, aux, chains=[0, C - 1])
 
 
+def test_reference_interface_liesel_pins_on_device(lb, golden_dir):
+    """reference tests/goose/test_interface_liesel.py:36-44 on the device: x = jax.random.normal(
+    PRNGKey(1337), (500,)) (regenerated through the restated JAX PRNG, committed as a fixture),
+    y = x ~ Normal(mu, 1): log_prob -719.46875 at mu = 0 and -25616.779296875 at mu = 10."""
+    import json
+    import os
+
+    fx = json.load(open(os.path.join(golden_dir, "interface_liesel.json")))
+    x = np.frombuffer(bytes.fromhex("".join(fx["x_float32_hex"])), dtype=np.float32).copy()
+    from liesel_b200.spec import ModelSpec
+
+    spec = ModelSpec(dtype=np.float32)
+    spec.add_response(x, "normal").add_predictor("loc")
+    spec.add_p_smooth(np.ones((x.size, 1), np.float32), 0.0, None, "loc", "mu")
+    spec.fixed_scale = 1.0
+    plan = lb.Plan(spec)
+    iface = lb.Interface(plan)
+    state = iface.initial_state(2, {"mu_beta": np.array([[0.0], [10.0]], np.float32)})
+    lp = iface.log_prob(state).cpu().numpy()
+    assert lp[0] == pytest.approx(fx["pins"]["log_prob_mu_0"])
+    assert lp[1] == pytest.approx(fx["pins"]["log_prob_mu_10"])
+    new_state = iface.update_state({"mu_beta": state["mu_beta"][[1, 0]].contiguous()}, state)  # update_state, :29-34
+    lp2 = iface.log_prob(new_state).cpu().numpy()
+    assert lp2[0] == pytest.approx(fx["pins"]["log_prob_mu_10"]) and lp2[1] == pytest.approx(fx["pins"]["log_prob_mu_0"])
+
+
 def test_unsorted_rows_same_result(lb):
     """Row order is free: the span-sorted plan and the plan in data order agree."""
     spec, centre = make("s2", np.float32)

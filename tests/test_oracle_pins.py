@@ -354,3 +354,35 @@ def test_centred_spline_equals_dense_centred_design():
     np.testing.assert_allclose(ia, ib, rtol=1e-9, atol=1e-9)
     # centred columns sum to zero over the rows: the constant direction is not identified
     assert np.abs((B - cbar).sum(axis=0)).max() < 1e-10
+
+
+# --- the reference's model-level pin behind jax.random (tests/goose/test_interface_liesel.py) ----
+def _interface_liesel_case(golden_dir):
+    fx = load(golden_dir, "interface_liesel.json")
+    x = np.frombuffer(bytes.fromhex("".join(fx["x_float32_hex"])), dtype=np.float32).copy()
+    spec = ModelSpec(dtype=np.float32)
+    spec.add_response(x, "normal").add_predictor("loc")          # y = x ~ Normal(mu, sigma = 1)
+    spec.add_p_smooth(np.ones((x.size, 1), np.float32), 0.0, None, "loc", "mu")  # mu: a Var without prior
+    spec.fixed_scale = 1.0
+    return fx, x, spec
+
+
+def test_threefry_known_answer_and_fixture_regenerates(golden_dir):
+    from oracle import jax_prng
+
+    a, b = jax_prng.threefry2x32(0x13198A2E, 0x03707344, np.array([0x243F6A88], np.uint32),
+                                 np.array([0x85A308D3], np.uint32))
+    assert (int(a[0]), int(b[0])) == (0xC4923A9C, 0x483DF7A0)  # Random123 known-answer vector
+    fx, x, _ = _interface_liesel_case(golden_dir)
+    np.testing.assert_array_equal(jax_prng.normal(jax_prng.prng_key(1337), 500), x)
+
+
+def test_interface_liesel_log_prob_pins(golden_dir):
+    """The oracle reproduces the two log-prob values the reference's own test asserts, on the inputs
+    that test creates with jax.random (same tolerance as there: pytest.approx, rel 1e-6)."""
+    fx, x, spec = _interface_liesel_case(golden_dir)
+    lp = sam.log_prob(spec, np.array([[0.0], [10.0]]))
+    assert lp[0] == pytest.approx(fx["pins"]["log_prob_mu_0"])
+    assert lp[1] == pytest.approx(fx["pins"]["log_prob_mu_10"])
+    g = sam.grad(spec, np.array([[0.0], [10.0]]))
+    np.testing.assert_allclose(g[:, 0], [x.astype(np.float64).sum(), x.astype(np.float64).sum() - 5000.0], rtol=1e-12)
