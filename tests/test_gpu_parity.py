@@ -180,6 +180,26 @@ def test_reference_interface_liesel_pins_on_device(lb, golden_dir):
     assert lp2[0] == pytest.approx(fx["pins"]["log_prob_mu_10"]) and lp2[1] == pytest.approx(fx["pins"]["log_prob_mu_0"])
 
 
+def test_reference_tutorial_01b_pins_on_device(lb, golden_dir):
+    """The whole-model log-probs that docs/source/tutorials/md/01b-model.md:213-277 prints (data from
+    numpy's default_rng(42)), through the C ABI in float32 and float64."""
+    import json
+    import os
+
+    from test_oracle_pins import tutorial_01b_spec
+
+    pin = json.load(open(os.path.join(golden_dir, "reference_pins.json")))["tutorial_01b_model"]
+    for dtype, rel in ((np.float32, 1e-6), (np.float64, 3e-7)):  # the printed values are float32
+        for key, s2 in (("sigma_sq_10", 10.0), ("sigma_sq_1", 1.0)):
+            spec = tutorial_01b_spec(pin, s2, dtype)
+            plan = lb.Plan(spec)
+            th = torch.zeros((3, 2), dtype=plan.dtype, device=plan.device)
+            lp, g = plan.logp_grad(th)
+            assert float(lp[0]) == pytest.approx(pin[key]["model_log_prob"], rel=rel)
+            lp_lik, _ = plan.logp_grad(th, flags=1)  # LSLB_SKIP_PRIOR: the response part alone
+            assert float(lp_lik[1]) == pytest.approx(pin[key]["y_log_prob_sum"], rel=rel)
+
+
 def test_unsorted_rows_same_result(lb):
     """Row order is free: the span-sorted plan and the plan in data order agree."""
     spec, centre = make("s2", np.float32)

@@ -386,3 +386,37 @@ def test_interface_liesel_log_prob_pins(golden_dir):
     assert lp[1] == pytest.approx(fx["pins"]["log_prob_mu_10"])
     g = sam.grad(spec, np.array([[0.0], [10.0]]))
     np.testing.assert_allclose(g[:, 0], [x.astype(np.float64).sum(), x.astype(np.float64).sum() - 5000.0], rtol=1e-12)
+
+
+# --- tutorial 01b: a whole model's log-prob, log-prior and log-lik as printed by the reference ----
+def tutorial_01b_spec(pin, sigma_sq, dtype=np.float32):
+    rng = np.random.default_rng(42)
+    n = pin["data"]["n"]
+    x0 = rng.uniform(size=n)
+    X = np.column_stack([np.ones(n), x0])
+    eps = rng.normal(scale=pin["data"]["true_sigma"], size=n)
+    y = X @ np.asarray(pin["data"]["true_beta"]) + eps
+    spec = ModelSpec(dtype=np.dtype(dtype))
+    spec.add_response(y, "normal").add_predictor("loc")
+    spec.add_p_smooth(X, 0.0, 100.0, "loc", "beta")
+    spec.fixed_scale = float(np.sqrt(sigma_sq))               # sigma = sqrt(sigma_sq), a Calc in the tutorial
+    spec.const_term = float(D.inverse_gamma_log_prob(sigma_sq, 0.01, 0.01))  # sigma_sq ~ InverseGamma(a, b)
+    return spec
+
+
+def test_tutorial_01b_model_log_prob_pins(golden_dir):
+    """docs/source/tutorials/md/01b-model.md prints model.log_prob / log_prior / log_lik and the
+    InverseGamma log-prob of sigma_sq for data from numpy's default_rng(42): float32 printouts,
+    compared at 7 significant digits."""
+    pin = load(golden_dir, "reference_pins.json")["tutorial_01b_model"]
+    th = np.array([pin["at_beta"]])
+    for key, s2 in (("sigma_sq_10", 10.0), ("sigma_sq_1", 1.0)):
+        spec = tutorial_01b_spec(pin, s2)
+        want = pin[key]
+        parts = sam.log_prob_parts(spec, th)
+        assert sam.log_prob(spec, th)[0] == pytest.approx(want["model_log_prob"], rel=3e-7)
+        assert parts["response"][0] == pytest.approx(want["y_log_prob_sum"], rel=3e-7)
+        assert D.inverse_gamma_log_prob(s2, 0.01, 0.01) == pytest.approx(want["sigma_sq_log_prob"], rel=1e-6)
+        if "log_prior" in want:
+            assert sam.log_prob(spec, th)[0] - parts["response"][0] == pytest.approx(want["log_prior"], rel=3e-7)
+            assert parts["response"][0] == pytest.approx(want["log_lik"], rel=3e-7)
