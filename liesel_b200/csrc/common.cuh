@@ -105,6 +105,8 @@ struct FinalizeParams {
   int nblocks;
   PriorP pr[LSLB_MAX_BLOCKS];
   int P, A, Psmall, C, Cpad, nchunks;
+  int nchunks_logp;  // slices whose log-likelihood rows are valid (<= nchunks): the tensor-core path's
+                     // K1 runs one CTA per SM over long row ranges, its K2 many short split-K chunks
   int Preal;  // rows [Preal, Psmall) of the small space are virtual (centring terms)
   double lik_const, const_term;
   unsigned flags;
@@ -258,7 +260,8 @@ struct BandedCfg {
 };
 struct TcCfg {
   int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;
-  int two_pass;  // drop the products with a lo factor of the large operands (see dense_tc_prepare)
+  int two_pass;  // bit 0 / bit 1: K1 / K2 drop the product with a lo factor of the large operand
+  int tiles_per_cta1, nchunks1;  // K1's own (coarse) row chunking: its accumulations are per tile
 };
 int dense_tc_prepare(lslb_plan* plan);                 // dense_tc.cu (called by lslb_plan_create)
 void dense_tc_release(lslb_plan* plan);

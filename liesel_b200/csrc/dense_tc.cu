@@ -616,6 +616,8 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C) {
   if (want < 1) want = 1;
   if (want > k.ntiles_rows) want = k.ntiles_rows;
   k.tiles_per_cta = (int)((k.ntiles_rows + want - 1) / want);
+  k.tiles_per_cta1 = k.tiles_per_cta;  // K1: one CTA per SM (each tile's eta is a fresh K = p accumulation)
+  k.nchunks1 = (k.ntiles_rows + k.tiles_per_cta1 - 1) / k.tiles_per_cta1;
   // K2 accumulates a CTA's whole row range in ONE fp32 TMEM accumulator, and the tensor core adds
   // into it with truncation: the bias grows with the number of MMAs in the chain (measured at
   // n = 6e5, 33k rows per CTA: a constant column used 2.1x the gradient tolerance). Shorter chains
@@ -669,17 +671,17 @@ static int tc_run(const lslb_plan* plan, const TcCfg& k, int C, const float* par
   const float fis = plan->fam == FAM_NORMAL_FIXED ? (float)(1.0 / plan->desc.fixed_scale) : 1.f;
   const size_t smem1 = tc::STAGES1 * sizeof(tc::K1Stage) + 4 * 128 * 32 * 4 + 1024;
   if (make_tmap_f32_k32(&mRT, RT, (n_pad / 32) * k.Cpad, 32, 32, tc::NC2) != LSLB_OK) return LSLB_ERR_CUDA;
-  dim3 grid1(k.ntiles_chain, k.nchunks);
+  dim3 grid1(k.ntiles_chain, k.nchunks1);
   if (g) {
     auto kern = tc::dense_tc_k1<FAM, true>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
-                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
+                                    p, k.tiles_per_cta1, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
   } else {
     auto kern = tc::dense_tc_k1<FAM, false>;
     LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     kern<<<grid1, 64 + 128 * tc::K1_GROUPS, smem1, st>>>(mPh, mPl, mXh, mXl, mRT, reinterpret_cast<const float*>(plan->desc.y), n, n_pad,
-                                    p, k.tiles_per_cta, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
+                                    p, k.tiles_per_cta1, k.ntiles_rows, fis, RT, partial, plan->Psmall, k.Cpad, k.two_pass);
   }
   LSLB_LAUNCH_CHECK();
   if (!g) return LSLB_OK;

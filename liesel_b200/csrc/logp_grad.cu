@@ -353,7 +353,7 @@ __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, con
   const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
   const T* lo = hi + fp.Cpad;
   double acc = 0.0;
-  for (int ch = g; ch < fp.nchunks; ch += FIN_G) acc += (double)hi[ch * stride] - (double)lo[ch * stride];
+  for (int ch = g; ch < fp.nchunks_logp; ch += FIN_G) acc += (double)hi[ch * stride] - (double)lo[ch * stride];
   // quadratic forms of the priors, coefficient rows j = g, g + FIN_G, ... (already scaled)
   if (with_prior) {
     const int cc = c < fp.C ? c : 0;
@@ -575,6 +575,7 @@ void fill_finalize_params(const lslb_plan* plan, FinalizeParams& fp, int C, int 
   fp.C = C;
   fp.Cpad = Cpad;
   fp.nchunks = nchunks;
+  fp.nchunks_logp = nchunks;
   fp.lik_const = plan->lik_const;
   fp.const_term = plan->desc.const_term;
   fp.flags = flags;
@@ -677,6 +678,7 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
 
   FinalizeParams fp;
   fill_finalize_params(plan, fp, C, k.Cpad, k.nchunks, flags);
+  if (tcp) fp.nchunks_logp = dense_tc_cfg(plan, C).nchunks1;
   EvalParams<T> ep;
   fill_eval_params<T>(plan, ep, C, k.Cpad);
   ep.pT = L.pT;
