@@ -222,8 +222,8 @@ int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int n
  *                      (LSLB_PEER_HANDLE_BYTES, HOST memory) to `handle`; synchronous.
  *   lslb_peer_connect: `handles` = the world's handles in rank order (HOST, world x 64 bytes),
  *                      exchanged by the caller (e.g. torch.distributed.all_gather); maps the peers.
- *   lslb_peer_timed_out: *timed_out != 0 when a wait for a peer exceeded ~2 s (results invalid);
- *                      synchronous, for tests and diagnostics.
+ *   lslb_peer_timed_out: *timed_out != 0 when a wait for a peer exceeded ~10 s; the outputs of such
+ *                      a call are NaN (never a silent partial sum). Synchronous, for diagnostics.
  */
 int lslb_peer_create(int rank, int world, size_t max_elems, lslb_peer** out, void* handle);
 int lslb_peer_connect(lslb_peer* peer, const void* handles);

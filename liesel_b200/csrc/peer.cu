@@ -98,12 +98,18 @@ peer_reduce_kernel(const __grid_constant__ PeerDev pd, T* __restrict__ out_a, si
     __threadfence_system();
     st_release_sys(pd.flag_at[threadIdx.x], pd.epoch);
   }
-  // wait until every rank published this epoch (bounded: ~2 s, then flag the error and go on)
+  // wait until every rank published this epoch. The wait is bounded (~10 s of SM clock): a rank that
+  // never arrives must not hang the GPU. A timed-out call is LOUD: the error flag is set and every
+  // output of this block becomes NaN (the reference's convention for a failed evaluation).
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
   if ((int)threadIdx.x < pd.world) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(pd.my_flags + threadIdx.x) - pd.epoch) < 0) {
-      if (clock64() - t0 > 4000000000LL) {
+      if (clock64() - t0 > 20000000000LL) {
         *pd.err = 1u;
+        timed_out = 1;
         break;
       }
       __nanosleep(64);
@@ -112,6 +118,12 @@ peer_reduce_kernel(const __grid_constant__ PeerDev pd, T* __restrict__ out_a, si
   __syncthreads();
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nth = (size_t)gridDim.x * blockDim.x;
+  if (timed_out) {
+    const T nan = (T)__int_as_float(0x7fc00000);
+    for (size_t i = tid; i < na; i += nth) out_a[i] = nan;
+    for (size_t i = tid; i < nb; i += nth) out_b[i] = nan;
+    return;
+  }
   reduce_region<T>(pd, 0, out_a, na, tid, nth);
   if (vec_b) {
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
