@@ -109,3 +109,32 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+
+
+def test_interface_protocol_mirrors_dict_interface_semantics():
+    """``extract_position`` / ``update_state`` of ``B200Interface`` behave like the reference's
+    ``DictInterface`` (reference tests/goose/test_interface_dict.py:24-56): key order follows the
+    request, the input state is never mutated, unknown keys are an error. (Pure host logic: a stand-in
+    plan carries the spec; ``log_prob`` itself needs the GPU and is covered by the GPU tests.)"""
+    import torch
+    from types import SimpleNamespace
+
+    from liesel_b200.interface import B200Interface
+
+    spec, _ = synth.s3_gamlss(n=50)
+    iface = B200Interface(SimpleNamespace(spec=spec))
+    keys = spec.position_keys() + spec.aux_keys()
+    state0 = {k: torch.full((2, 3), float(i)) for i, k in enumerate(keys)}
+    pos = iface.extract_position([keys[1], keys[0]], state0)
+    assert list(pos.keys()) == [keys[1], keys[0]] and len(pos) == 2
+    assert pos[keys[0]] is state0[keys[0]]
+    new = torch.ones((2, 3))
+    state1 = iface.update_state({keys[0]: new}, state0)
+    assert state1[keys[0]] is new and state0[keys[0]] is not new          # functional update
+    assert set(state1) == set(state0)
+    with pytest.raises(KeyError):
+        iface.update_state({"not_a_variable": new}, state0)
+    with pytest.raises(KeyError):
+        iface.extract_position(["not_a_variable"], state0)
+    with pytest.raises(KeyError):
+        iface.chol_info_fn("not_a_variable")
