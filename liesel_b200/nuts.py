@@ -192,6 +192,18 @@ class BatchedNUTS:
     def _da_finalize(self):
         self.step_size = torch.exp(self.da_log_avg)
 
+    # -- the two per-leaf kernels (hooks: the CPU tests substitute torch restatements to exercise the
+    #    subtree bookkeeping, compaction included, without a GPU) ------------------------------------
+    def _leaf_pre(self, fn, st, ptrs, ints, stream, leaf):
+        from . import _lib
+
+        _lib.check(fn(ptrs, ints, stream), "lslb_nuts_leaf_pre")
+
+    def _leaf_post(self, fn, st, ptrs, ints, stream, leaf):
+        from . import _lib
+
+        _lib.check(fn(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+
     # -- fused subtree (CUDA kernels for the per-leaf bookkeeping) ----------------------------------
     def _subtree_fused(self, j, q_e, r_e, g_e, eps, h0, alive, lp_prop, U, ck_r, ck_s):
         import ctypes as Ct
@@ -261,12 +273,12 @@ class BatchedNUTS:
         ints = (Ct.c_int * 6)(Cb, P, st["ck_r"].shape[1], 0, 0, 0)
 
         def run_leaves(i0, i1):
-            stream = _lib.stream_ptr()
+            stream = _lib.stream_ptr() if dev.type == "cuda" else None
             for i in range(i0, i1):
                 lo, hi = _leaf_idx_to_ckpt_idxs(i)
                 ints[3], ints[4], ints[5] = i & 1, lo, hi
                 ptrs[22] = st["U"][i].data_ptr()
-                _lib.check(pre(ptrs, ints, stream), "lslb_nuts_leaf_pre")
+                self._leaf_pre(pre, st, ptrs, ints, stream, i)
                 if self.f_into is not None:
                     if idx is None:
                         self.f_into(st["q_n"], st["lp_n"], st["g_n"])
@@ -275,7 +287,7 @@ class BatchedNUTS:
                 else:
                     lp, g = self.f(st["q_n"])
                     st["lp_n"].copy_(lp); st["g_n"].copy_(g)
-                _lib.check(post(ptrs, ints, self.div_thr, stream), "lslb_nuts_leaf_post")
+                self._leaf_post(post, st, ptrs, ints, stream, i)
 
         def flush():
             """Results of the current batch rows -> full-size outputs (real rows only)."""

@@ -162,3 +162,101 @@ def test_hmc_nan_energy_is_divergent_and_rejected():
     bad = info.divergent
     assert torch.equal(s.q[bad], q_before[bad])
     assert (info.acceptance_prob[bad] == 0).all() and (info.error_code[bad] == 1).all()
+
+
+# --- the fused subtree bookkeeping (and chain compaction) on CPU --------------------------------
+class TorchLeafNUTS(nuts.BatchedNUTS):
+    """BatchedNUTS whose two per-leaf CUDA kernels (csrc/nuts.cu) are replaced by torch restatements
+    acting on the same state buffers, so that the fused driver — buffer management, leaf ranges,
+    checkpoints, compaction — runs without a GPU."""
+
+    def _leaf_pre(self, fn, st, ptrs, ints, stream, leaf):
+        Cb = ints[0]
+        e = st["eps"][:Cb, None]
+        rh = st["r_e"][:Cb] + 0.5 * e * st["g_e"][:Cb]
+        st["r_half"][:Cb] = rh
+        st["q_n"][:Cb] = st["q_e"][:Cb] + e * (st["inv_mass"][:Cb] * rh)
+
+    def _leaf_post(self, fn, st, ptrs, ints, stream, leaf):
+        Cb, odd, lo, hi = ints[0], ints[3], ints[4], ints[5]
+        v = lambda k: st[k][:Cb]
+        e, im = v("eps")[:, None], v("inv_mass")
+        rn = v("r_half") + 0.5 * e * v("g_n")
+        st["r_half"][:Cb] = rn
+        act = v("act").bool()
+        kin = 0.5 * (im * rn * rn).sum(dim=1)
+        dh = torch.nan_to_num((-v("lp_n") + kin) - v("h0"), nan=float("inf"))
+        div = dh > self.div_thr
+        logw_n = -dh
+        acc = torch.exp(torch.clamp(-dh, max=0.0))
+        lw_new = torch.logaddexp(v("logw_s"), logw_n)
+        take = act & (torch.log(st["U"][leaf][:Cb]) < logw_n - lw_new)
+        rs = v("rsum_s") + rn
+        turning = torch.zeros(Cb, dtype=torch.bool)
+        if odd:
+            for k in range(hi, lo - 1, -1):
+                rl = v("ck_r")[:, k]
+                sub = rs - v("ck_s")[:, k] + rl
+                rho = sub - 0.5 * (rn + rl)
+                turning |= ((im * rl * rho).sum(dim=1) <= 0) | ((im * rn * rho).sum(dim=1) <= 0)
+        m = act[:, None]
+        st["rsum_s"][:Cb] = torch.where(m, rs, v("rsum_s"))
+        for dst, src in (("q_s", "q_n"), ("g_s", "g_n")):
+            st[dst][:Cb] = torch.where(take[:, None], v(src), v(dst))
+        for dst, src in (("q_e", v("q_n")), ("r_e", rn), ("g_e", v("g_n"))):
+            st[dst][:Cb] = torch.where(m, src, v(dst))
+        if not odd:
+            st["ck_r"][:Cb, hi] = torch.where(m, rn, v("ck_r")[:, hi])
+            st["ck_s"][:Cb, hi] = torch.where(m, rs, v("ck_s")[:, hi])
+        st["lp_s"][:Cb] = torch.where(take, v("lp_n"), v("lp_s"))
+        st["logw_s"][:Cb] = torch.where(act, lw_new, v("logw_s"))
+        st["sum_acc"][:Cb] = v("sum_acc") + torch.where(act, acc, torch.zeros_like(acc))
+        st["n_leaf"][:Cb] = v("n_leaf") + act.to(v("n_leaf").dtype)
+        d = v("div_s").bool() | (act & div)
+        t = v("turn_s").bool() | (act & turning)
+        st["div_s"][:Cb] = d.to(torch.uint8)
+        st["turn_s"][:Cb] = t.to(torch.uint8)
+        st["act"][:Cb] = (act & ~(d | t)).to(torch.uint8)
+
+
+def test_fused_subtree_and_compaction_on_cpu():
+    """The fused driver (with the kernels restated in torch) reproduces the plain torch path draw for
+    draw, with and without dropping terminated chains from the batch; per-chain step sizes give the
+    heterogeneous tree depths that make compaction kick in."""
+    C, P = 200, 6
+    scale = torch.linspace(0.5, 3.0, P, dtype=torch.float64)
+
+    def f(q):
+        return -0.5 * ((q / scale) ** 2).sum(dim=1), -q / scale**2
+
+    seen = []
+
+    def into(q, lp, g, chains=None):
+        seen.append(q.shape[0])
+        a, b = f(q)
+        lp.copy_(a)
+        g.copy_(b)
+
+    q0 = torch.randn(C, P, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    kw = dict(seed=11, initial_step_size=0.1, max_treedepth=7)
+    ref = nuts.BatchedNUTS(f, q0, fused=False, **kw)
+    fus = TorchLeafNUTS(f, q0, fused=True, logp_grad_into=into, **kw)
+    cmp_ = TorchLeafNUTS(f, q0, fused=True, logp_grad_into=into, compact=True, **kw)
+    assert cmp_.compact and not fus.compact
+    eps = 0.05 * torch.pow(torch.tensor(2.0, dtype=torch.float64), torch.arange(C, dtype=torch.float64) % 5)
+    for s in (ref, fus, cmp_):
+        s.step_size = eps.clone()
+    for _ in range(5):
+        i_ref, i_fus = ref.transition(), fus.transition()
+        seen.clear()
+        i_cmp = cmp_.transition()
+        for info, s in ((i_fus, fus), (i_cmp, cmp_)):
+            assert torch.equal(info.treedepth, i_ref.treedepth)
+            assert torch.equal(info.error_code, i_ref.error_code)
+            assert torch.equal(info.leapfrog, i_ref.leapfrog)
+            np.testing.assert_allclose(info.acceptance_prob.numpy(), i_ref.acceptance_prob.numpy(), rtol=1e-10)
+            np.testing.assert_allclose(s.q.numpy(), ref.q.numpy(), rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(s.logp.numpy(), ref.logp.numpy(), rtol=1e-10)
+        assert min(seen) < C and all(b % 64 == 0 or b == C for b in seen)  # compacted, padded to 64
+    assert int(i_ref.treedepth.max()) > int(i_ref.treedepth.min())
+    assert cmp_.evals == fus.evals and cmp_.chain_evals < 0.9 * fus.chain_evals
