@@ -9,6 +9,17 @@ the data. One evaluation = (log-posterior, full gradient) of ONE chain over ALL 
 counts 1024 evaluations per GPU. Multi-GPU: chains are sharded (each rank holds a replica of the
 44 MB data set and its own 1024 chains), no data-path collective -> "scaling": "weak".
 
+The same JSON line carries, beside the headline keys:
+  "ess"        (N = 1) the second half of the metric: NUTS-within-Gibbs on H (reference NUTSKernel
+               defaults, Stan-style warm-up), min bulk-ESS of the posterior draws / posterior
+               seconds, split-R-hat, SM clock over the run, and a CPU arm (the same sampler on the
+               oracle's CPU port, host cores stated);
+  "secondary"  other BASELINE.json configs through the same C ABI: at N = 1 the per-config
+               timings S2 / S3 (+ IWLS pass) / S4 shard / S5; at N > 1 H with the 1024 chains
+               STRONG-scaled over the ranks and S4 with the data ROWS sharded (1.25e6 rows per
+               rank) and the [C x (P+1)] partials summed inside the C call over NCCL
+               (lslb_logp_grad_nccl_f32) and over NVLink peer memory (lslb_logp_grad_peer_f32).
+
   python bench.py --gpus 1 --steps 20 --warmup 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
   python bench.py --impl reference ...   # CPU arm: the oracle's port of the reference algorithm
@@ -45,6 +56,13 @@ def parse_args():
     ap.add_argument("--chains", type=int, default=1024, help="chains per GPU")
     ap.add_argument("--cpu-chains", type=int, default=64, help="chains in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the per-config / sharded entries")
+    ap.add_argument("--no-ess", action="store_true", help="skip the NUTS ESS/sec run")
+    ap.add_argument("--ess-chains", type=int, default=1024)
+    ap.add_argument("--ess-warmup", type=int, default=1000, help="reference default warm-up duration")
+    ap.add_argument("--ess-samples", type=int, default=500)
+    ap.add_argument("--ess-cpu-chains", type=int, default=64)
+    ap.add_argument("--ess-cpu-seconds", type=float, default=25.0)
     return ap.parse_args()
 
 
@@ -214,6 +232,236 @@ def measure_pipe_peaks(torch, _lib, sm_count):
     }
 
 
+
+# ----------------------------------------------------------------------------------------------
+# secondary entries and the ESS run
+# ----------------------------------------------------------------------------------------------
+def timed_calls(torch, dist, fn, reps, flush, world, dev, warm=3):
+    """Mean ms per call over `reps` calls (L2 flushed before each, CUDA events on the current
+    stream, barrier + synchronize on both sides), max over ranks."""
+    for _ in range(warm):
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# SURVEY 8(d): algorithmic flops per batched call (C evaluations) of the secondary configs
+def _flops(name, n, C, p=0):
+    per_row = {"S2": 16 * 5 + 12, "S3": 16 * 2 + 14, "S3_iwls": 8 + 8 + 20 + 8 + 14,
+               "S4": 4 * p + 12, "S5": 4 * 8 + 10}[name]
+    return float(n) * C * per_row
+
+
+def secondary_single_gpu(torch, dist, dev, flush, fp32_peak, tf32x3_note, reps=10):
+    """S2, S3 (+ one IWLS pass), one S4 shard and S5 at BASELINE.json's sizes on one GPU."""
+    from liesel_b200 import synth
+    from liesel_b200.plan import Plan
+
+    out = []
+    cfgs = [
+        ("S2", lambda: synth.s2_pspline_gam(n=100_000), 64, "loc_np0", "P-spline GAM, 5 cubic smooths x 20, n=1e5, 64 chains"),
+        ("S3", lambda: synth.s3_gamlss(n=1_000_000), 256, "loc_np0", "Gaussian location-scale GAMLSS, n=1e6, 256 chains"),
+        ("S4", lambda: synth.s4_logistic(n=10_000_000, world_size=8), 1024, None,
+         "logistic regression p=256: ONE rank's shard of n=1e7 (1.25e6 rows), 1024 chains, no collective at N=1"),
+        ("S5", lambda: synth.s5_poisson_ri(n=5_000_000, G=100_000), 1024, None,
+         "Poisson random intercept, G=1e5, n=5e6, 1024 chains"),
+    ]
+    for name, make, C, iwls_block, what in cfgs:
+        spec, centre = make()
+        plan = Plan(spec, device=dev)
+        th, aux = synth.evaluation_points(spec, centre, C)
+        t = torch.as_tensor(th, device=dev)
+        a = torch.as_tensor(aux, device=dev) if spec.num_aux else None
+        ms = timed_calls(torch, dist, lambda: plan.logp_grad(t, a), reps, flush, 1, dev)
+        ent = {"name": name, "workload": what, "n": spec.n, "chains": C, "P": plan.P,
+               "kernel": plan.kernel_name(C), "variant": plan.variant, "ms_per_call": ms,
+               "evals_per_s": C / (ms * 1e-3)}
+        p_dense = plan.P if name == "S4" else 0
+        fl = _flops(name, spec.n, C, p_dense)
+        ent["algorithmic_flops_per_call"] = fl
+        ent["achieved_tflops"] = fl / (ms * 1e-3) / 1e12
+        if name == "S4":
+            ent["roofline_note"] = tf32x3_note
+        else:
+            ent["frac_of_fp32_peak"] = ent["achieved_tflops"] / fp32_peak
+        if iwls_block:
+            ms_i = timed_calls(torch, dist, lambda: plan.iwls(iwls_block, t, a), reps, flush, 1, dev)
+            ent["iwls"] = {"block": iwls_block, "ms_per_pass": ms_i, "passes_per_s": C / (ms_i * 1e-3),
+                           "what": "score + observed information + ridge + Cholesky of one coefficient block"}
+            if name == "S3":
+                fi = _flops("S3_iwls", spec.n, C)
+                ent["iwls"]["frac_of_fp32_peak"] = fi / (ms_i * 1e-3) / 1e12 / fp32_peak
+        out.append(ent)
+        del plan, t, a
+        torch.cuda.empty_cache()
+    return out
+
+
+def secondary_multi_gpu(torch, dist, dev, flush, rank, world, K, h_plan, h_spec, h_centre, total_chains=1024):
+    """N > 1: (1) H strong-scaled (1024 chains in total, data replicated, no collective);
+    (2) S4 with the ROWS sharded, 1.25e6 rows per rank (n = 1e7 at N = 8, BASELINE config 4): every
+    rank evaluates all 1024 chains on its rows and the [C x (P+1)] partials are summed over the ranks
+    inside the C call, over NCCL and over NVLink peer memory."""
+    from liesel_b200 import dist as ld
+    from liesel_b200 import synth
+    from liesel_b200.plan import Plan
+
+    out = []
+    # -- (1) strong scaling of the headline -----------------------------------------------------
+    a0, a1 = ld.chain_shard(total_chains, rank, world)
+    th, aux = synth.evaluation_points(h_spec, h_centre, total_chains, seed=777)
+    t = torch.as_tensor(th[a0:a1], device=dev).contiguous()
+    a = torch.as_tensor(aux[a0:a1], device=dev).contiguous()
+    lp = torch.empty(a1 - a0, dtype=torch.float32, device=dev)
+    g = torch.empty((a1 - a0, h_plan.P), dtype=torch.float32, device=dev)
+    ms = timed_calls(torch, dist, lambda: h_plan.logp_grad(t, a, out=(lp, g)), K, flush, world, dev)
+    out.append({"name": "H_strong_scaling", "scaling": "strong",
+                "workload": f"H (n={h_spec.n}) with {total_chains} chains IN TOTAL, {a1 - a0} per GPU, data replicated",
+                "chains_total": total_chains, "chains_per_gpu": a1 - a0, "kernel": h_plan.kernel_name(a1 - a0),
+                "ms_per_call": ms, "evals_per_s": total_chains / (ms * 1e-3), "collective": None})
+    del t, a, lp, g
+
+    # -- (2) S4 row-sharded -------------------------------------------------------------------
+    rows_per_rank, p, C = 1_250_000, 256, 1024
+    n_total = rows_per_rank * world
+    spec, centre = synth.s4_logistic(n=n_total, p=p, rank=rank, world_size=world)
+    plan = Plan(spec, device=dev)
+    th, _ = synth.evaluation_points(spec, centre, C)
+    t = torch.as_tensor(th, device=dev)
+    flags = 0 if rank == 0 else ld.SKIP_PRIOR
+    base = {"workload": (f"S4 logistic regression, n={n_total} rows sharded over {world} GPUs "
+                         f"({rows_per_rank} per rank), p={p}, {C} chains on every rank"),
+            "scaling": "weak in rows (BASELINE config 4 at N=8)", "n_total": n_total, "chains": C,
+            "kernel": plan.kernel_name(C), "variant": plan.variant,
+            "exchange_bytes_per_call": C * (p + 1) * 4}
+    # rank-local partial sums, then the reference sum over ranks through torch.distributed
+    ms_local = timed_calls(torch, dist, lambda: plan.logp_grad(t, None, flags=flags), K, flush, world, dev)
+    lp_l, g_l = plan.logp_grad(t, None, flags=flags)
+    ref = torch.cat([lp_l[:, None], g_l], dim=1).double()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+    out.append(dict(base, name="S4_rowshard_local_only", transport=None, ms_per_call=ms_local,
+                    note="each rank's partial evaluation without the sum over ranks (max over ranks)"))
+    for name, make in (("nccl", lambda: ld.NcclComm(dev)), ("peer", lambda: ld.PeerGroup(C * (p + 1), dev))):
+        try:
+            sh = make()
+            ms_t = timed_calls(torch, dist, lambda: plan.logp_grad(t, None, flags=flags, shard=sh), K, flush, world, dev)
+            lp_s, g_s = plan.logp_grad(t, None, flags=flags, shard=sh)
+            got = torch.cat([lp_s[:, None], g_s], dim=1).double()
+            err = (got - ref).abs().max()
+            rel = ((got - ref).abs() / ref.abs().clamp_min(1e-30)).max()
+            stat = torch.stack([err, rel])
+            dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+            ent = dict(base, name=f"S4_rowshard_{name}", transport=name,
+                       entry_point=f"lslb_logp_grad_{name}_f32", ms_per_call=ms_t,
+                       evals_per_s=C / (ms_t * 1e-3), exchange_ms=max(ms_t - ms_local, 0.0),
+                       max_abs_diff_vs_rank_local_sums=float(stat[0]), max_rel_diff=float(stat[1]))
+            if name == "peer":
+                ent["timed_out"] = bool(sh.timed_out())
+            out.append(ent)
+            torch.cuda.synchronize()
+            dist.barrier()
+            sh.close()
+        except Exception as e:  # a transport that cannot be set up is reported, not fatal
+            out.append(dict(base, name=f"S4_rowshard_{name}", transport=name, error=repr(e)[:300]))
+    del plan, t
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ess(args, torch, dev, plan, spec, centre, local):
+    """NUTS-within-Gibbs on H: all coefficients in one NUTS block (reference NUTSKernel defaults:
+    max_treedepth 10, target acceptance 0.8, diagonal mass matrix, Stan-style warm-up epochs), tau2
+    by its Gibbs full conditional after every transition; both smooths under the sum-to-zero
+    constraint (liesel_b200/reparam.py). ESS = min over coordinates of bulk-ESS of all posterior draws."""
+    from liesel_b200 import reparam, synth
+    from liesel_b200.nuts_gibbs import NutsGibbs, PlanEvaluator, summarise
+
+    C, W, S = args.ess_chains, args.ess_warmup, args.ess_samples
+    cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
+    rep = reparam.sum_to_zero(spec, cm, device=dev)
+    th0, aux0 = synth.evaluation_points(spec, centre, C, seed=1)
+    sampler = ClockSampler(local)
+    sampler.wait_started()
+    t0 = time.perf_counter()
+    run = NutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev),
+                    torch.as_tensor(aux0, device=dev), reparam=rep, seed=1, compact=True)
+    winfo = run.warmup(W)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    draws, infos = run.sample(S)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    clocks = sampler.stop()
+    out = summarise(draws, infos, t2 - t1, t1 - t0)
+    nuts = run.nuts
+    out.update({
+        "sampler": ("one NUTS block over all coefficients + Gibbs draw of every tau2 per transition; "
+                    "reference defaults (max_treedepth 10, target accept 0.8, diagonal mass matrix, "
+                    "Stan-style warm-up epochs), finished chains dropped from the batched evaluation"),
+        "model": workload_name(spec.n, C).replace(" per GPU", ""),
+        "constraint": "sum-to-zero on both smooths (beta = Z gamma, 2 x 19 + 2 = 40 sampled coordinates)",
+        "warmup_iters": W, "posterior_iters": S,
+        "warmup_mean_treedepth": float(np.mean([float(i.treedepth.float().mean()) for i in winfo])),
+        "batched_evals_warmup": int(sum(i.evaluations for i in winfo)),
+        "step_size_median": float(nuts.step_size.median()),
+        "mean_batch_fill": float(nuts.chain_evals) / max(1.0, float(nuts.evals) * C),
+        "clocks": clocks,
+    })
+    # ---- CPU arm: the same sampler on the oracle's CPU port, host cores ----------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle.cpu_port import CpuEvaluator
+
+        Cc = min(args.ess_cpu_chains, C)
+        torch.set_num_threads(os.cpu_count() or 1)
+        ev = CpuEvaluator(spec)
+        rep_c = reparam.sum_to_zero(spec, cm)
+        q_full = run.full(nuts.q[:Cc]).cpu()
+        run_c = NutsGibbs(spec, ev, q_full, run.aux[:Cc].cpu(), reparam=rep_c, seed=2,
+                          initial_step_size=1.0, fused=False)
+        # adapted state of the GPU run's first Cc chains: the CPU arm times POSTERIOR transitions
+        run_c.nuts.step_size = nuts.step_size[:Cc].cpu().clone()
+        run_c.nuts.inv_mass = nuts.inv_mass[:Cc].cpu().clone()
+        ev0 = run_c.nuts.evals
+        tc0 = time.perf_counter()
+        iters = 0
+        while iters < 2 or (time.perf_counter() - tc0 < args.ess_cpu_seconds and iters < S):
+            run_c.nuts.transition()
+            run_c._gibbs(run_c.nuts)
+            iters += 1
+        dtc = time.perf_counter() - tc0
+        ess_per_draw_chain = out["ess_bulk_min"] / (S * C)
+        cpu = {
+            "kind": "port", "cores": ev.port.threads, "chains": Cc, "transitions_timed": iters,
+            "seconds": dtc, "seconds_per_transition": dtc / iters,
+            "batched_evals": int(run_c.nuts.evals - ev0),
+            "ess_per_sec_posterior": ess_per_draw_chain * Cc * iters / dtc,
+            "how": ("real NUTS+Gibbs transitions on oracle/cpu_port.py (torch CPU fp32, all host threads) from "
+                    "the GPU run's adapted state (positions, step sizes, mass matrices of its first "
+                    f"{Cc} chains); ESS per draw and chain ({ess_per_draw_chain:.3f}) is the GPU run's — same "
+                    "sampler, same model — because a CPU run long enough to estimate ESS itself does not "
+                    "fit the bench budget; bounded sample of the 1024-chain workload"),
+        }
+    out["cpu_arm"] = cpu
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -330,6 +578,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = C_ * world * K / (float(t.item()) * 1e-3)
 
+    secondary = []
+    if world > 1 and not args.no_secondary:
+        secondary = secondary_multi_gpu(torch, dist, dev, flush, rank, world, K, plan, spec, centre)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,13 +607,15 @@ def run_ours(args):
     except (OSError, ValueError):
         pass
     roofline = {
-        "kernel": "lslb::eval_kernel (variant %s)" % plan.variant,
+        "kernel": plan.kernel_name(C_) + "<FAM_NORMAL_LS, NS=2, PM=2, GRAD, UNITY> (ncu: lslb::banded_x2_kernel<0,2,2,1,1>)"
+        if plan.kernel_name(C_) == "lslb::banded_x2_kernel" else plan.kernel_name(C_),
         "bound": "fp32_simt",
         "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
         "peak_source": "FP32 FMA micro-benchmark run live in this process (lslb_debug_pipe_peak)",
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_alg,
         "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (total_ms / K),
         "traffic": traffic,
+        "traffic_source": "ncu --set full capture of this command, committed as profiles/traffic.json (offline, not measured in this run)",
         "hbm": {"achieved": bytes_alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
         "pipe_peaks_measured": pipe,
@@ -373,6 +626,20 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_sample(spec, centre, args.cpu_chains)
+    if world == 1 and not args.no_secondary:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        bf16 = float(mp.get("bf16_tflops_sustained", mp.get("bf16_tflops", 0.0)) or 0.0)
+        note = ("tensor pipe: eta = X B and G = X^T R as tcgen05 kind::tf32 GEMMs in split precision "
+                "(2 + 3 passes for rtol 1e-5); executed tensor flops = 2.5 x the algorithmic 4 n p C; TF32 "
+                f"dense rate = half the bf16 rate (MEASURED_PEAKS.json sustained bf16 {bf16:.0f} TFLOP/s)")
+        secondary = secondary_single_gpu(torch, dist, dev, flush, fp32_peak, note)
+        for ent in secondary:
+            if ent["name"] == "S4" and bf16 > 0:
+                ent["frac_of_tf32_split_bound"] = 2.5 * ent["achieved_tflops"] / (0.5 * bf16)
+    ess = None
+    if world == 1 and not args.no_ess:
+        ess = run_ess(args, torch, dev, plan, spec, centre, local)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -390,6 +657,8 @@ def run_ours(args):
         "gpu_launches": int(3 * K),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "ess": ess,
+        "secondary": secondary,
         "wall_s_timed_region_incl_flush": wall,
     }
     print(json.dumps(line), flush=True)

@@ -132,8 +132,15 @@ int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out);
 void lslb_plan_destroy(lslb_plan* plan);
 int lslb_plan_num_params(const lslb_plan* plan);
 int lslb_plan_num_aux(const lslb_plan* plan);
+/* LSLB_F32 / LSLB_F64 of the plan's data and parameters (-1 for a NULL plan); number of
+ * coefficients of block `block` (-1 when out of range). Used by bindings to check operand shapes. */
+int lslb_plan_dtype(const lslb_plan* plan);
+int lslb_plan_block_ncoef(const lslb_plan* plan, int block);
 /* Name of the kernel variant the plan dispatches to (static string). */
 const char* lslb_plan_variant(const lslb_plan* plan);
+/* Symbol name (as ncu prints it, without template arguments) of the row-streaming kernel that
+ * lslb_logp_grad_* launches for C chains on this plan (static string; "" for a NULL plan). */
+const char* lslb_plan_kernel_name(const lslb_plan* plan, int C);
 
 /* Bytes of device scratch a compute call on C chains needs (max over all entry points). */
 size_t lslb_workspace_bytes(const lslb_plan* plan, int C);
@@ -176,6 +183,21 @@ int lslb_quadform_f32(const lslb_plan* plan, int C, int block, const float* para
                       float* out, lslb_stream_t stream);
 int lslb_quadform_f64(const lslb_plan* plan, int C, int block, const double* params,
                       double* out, lslb_stream_t stream);
+
+/*
+ * Metropolis-Hastings step per chain (goose/mh.py:48-68), with the state selection fused:
+ *   log_acc = prop_lp - cur_lp + log_corr   (log_corr == NULL: 0);  NaN -> -inf and code 90
+ *   acc = min(exp(log_acc), 1);  moved = (u <= acc)
+ * On acceptance cur_lp[c] = prop_lp[c] and (when given) row c of params [C x P] is replaced by row
+ * c of params_prop. u, cur_lp, prop_lp, log_corr, acc are [C]; code int32 [C]; moved uint8 [C];
+ * code / acc / moved / params may be NULL.
+ */
+int lslb_mh_step_f32(int C, int P, const float* u, float* cur_lp, const float* prop_lp,
+                     const float* log_corr, float* params, const float* params_prop, int* code,
+                     float* acc, unsigned char* moved, lslb_stream_t stream);
+int lslb_mh_step_f64(int C, int P, const double* u, double* cur_lp, const double* prop_lp,
+                     const double* log_corr, double* params, const double* params_prop, int* code,
+                     double* acc, unsigned char* moved, lslb_stream_t stream);
 
 /*
  * IWLS proposal tail per chain (iwls.py:323-327 and :335-336; iwls_utils.py:14-70):
@@ -222,13 +244,25 @@ int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int n
  *                      (LSLB_PEER_HANDLE_BYTES, HOST memory) to `handle`; synchronous.
  *   lslb_peer_connect: `handles` = the world's handles in rank order (HOST, world x 64 bytes),
  *                      exchanged by the caller (e.g. torch.distributed.all_gather); maps the peers.
- *   lslb_peer_timed_out: *timed_out != 0 when a wait for a peer exceeded ~10 s; the outputs of such
- *                      a call are NaN (never a silent partial sum). Synchronous, for diagnostics.
+ *   lslb_peer_timed_out: *timed_out != 0 when this rank's group has FAILED: a wait for a peer
+ *                      exceeded ~10 s, a peer reported failure, or lslb_peer_abort was called. A
+ *                      failure is fatal for the whole group: the failing rank writes a poison value
+ *                      into its flag on every peer, so each rank's current or next sharded call
+ *                      returns NaN outputs (never a silent partial sum) and every later call does
+ *                      too, until lslb_peer_reset. Synchronous, for diagnostics.
+ *   lslb_peer_abort  : fails the group from the host side (asynchronous on `stream`). The sharded
+ *                      entry points do this themselves when their evaluation cannot be launched
+ *                      after the exchange slot was claimed, and then return LSLB_ERR_COMM until reset.
+ *   lslb_peer_reset  : clears flags, error word and epoch of THIS rank. Collective: every rank
+ *                      must call it, with a host barrier before (no sharded call in flight
+ *                      anywhere) and after (nobody publishes into a buffer that is not reset yet).
  */
 int lslb_peer_create(int rank, int world, size_t max_elems, lslb_peer** out, void* handle);
 int lslb_peer_connect(lslb_peer* peer, const void* handles);
 void lslb_peer_destroy(lslb_peer* peer);
 int lslb_peer_timed_out(lslb_peer* peer, int* timed_out);
+int lslb_peer_abort(lslb_peer* peer, lslb_stream_t stream);
+int lslb_peer_reset(lslb_peer* peer);
 int lslb_logp_grad_peer_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
                             float* logp, float* grad, uint32_t flags, void* ws, size_t ws_bytes,
                             lslb_peer* peer, lslb_stream_t stream);

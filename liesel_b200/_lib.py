@@ -63,8 +63,14 @@ lib.lslb_plan_num_params.restype = _i
 lib.lslb_plan_num_params.argtypes = [_vp]
 lib.lslb_plan_num_aux.restype = _i
 lib.lslb_plan_num_aux.argtypes = [_vp]
+lib.lslb_plan_dtype.restype = _i
+lib.lslb_plan_dtype.argtypes = [_vp]
+lib.lslb_plan_block_ncoef.restype = _i
+lib.lslb_plan_block_ncoef.argtypes = [_vp, _i]
 lib.lslb_plan_variant.restype = C.c_char_p
 lib.lslb_plan_variant.argtypes = [_vp]
+lib.lslb_plan_kernel_name.restype = C.c_char_p
+lib.lslb_plan_kernel_name.argtypes = [_vp, _i]
 lib.lslb_workspace_bytes.restype = _sz
 lib.lslb_workspace_bytes.argtypes = [_vp, _i]
 for _sfx in ("f32", "f64"):
@@ -83,6 +89,9 @@ for _sfx in ("f32", "f64"):
     f = getattr(lib, "lslb_iwls_propose_" + _sfx)
     f.restype = _i
     f.argtypes = [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    f = getattr(lib, "lslb_mh_step_" + _sfx)
+    f.restype = _i
+    f.argtypes = [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     f = getattr(lib, "lslb_spline_basis_" + _sfx)
     f.restype = _i
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
@@ -104,6 +113,10 @@ lib.lslb_peer_destroy.restype = None
 lib.lslb_peer_destroy.argtypes = [_vp]
 lib.lslb_peer_timed_out.restype = _i
 lib.lslb_peer_timed_out.argtypes = [_vp, C.POINTER(_i)]
+lib.lslb_peer_abort.restype = _i
+lib.lslb_peer_abort.argtypes = [_vp, _vp]
+lib.lslb_peer_reset.restype = _i
+lib.lslb_peer_reset.argtypes = [_vp]
 lib.lslb_nccl_unique_id.restype = _i
 lib.lslb_nccl_unique_id.argtypes = [_vp]
 lib.lslb_nccl_comm_create.restype = _i
@@ -131,7 +144,7 @@ lib.lslb_debug_tc_probe.restype = _i
 lib.lslb_debug_tc_probe.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
 
 EXPORTS = [
-    "lslb_peer_create", "lslb_peer_connect", "lslb_peer_destroy", "lslb_peer_timed_out",
+    "lslb_peer_create", "lslb_peer_connect", "lslb_peer_destroy", "lslb_peer_timed_out", "lslb_peer_abort", "lslb_peer_reset",
     "lslb_logp_grad_peer_f32", "lslb_logp_grad_peer_f64", "lslb_iwls_peer_f32", "lslb_iwls_peer_f64",
     "lslb_nccl_unique_id", "lslb_nccl_comm_create", "lslb_nccl_comm_destroy",
     "lslb_logp_grad_nccl_f32", "lslb_logp_grad_nccl_f64", "lslb_iwls_nccl_f32", "lslb_iwls_nccl_f64",
@@ -139,10 +152,10 @@ EXPORTS = [
     "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
     "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
-    "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_variant",
+    "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_dtype", "lslb_plan_block_ncoef", "lslb_plan_variant", "lslb_plan_kernel_name",
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",
     "lslb_iwls_f64", "lslb_chol_f32", "lslb_chol_f64", "lslb_quadform_f32", "lslb_quadform_f64",
-    "lslb_iwls_propose_f32", "lslb_iwls_propose_f64", "lslb_spline_basis_f32",
+    "lslb_iwls_propose_f32", "lslb_iwls_propose_f64", "lslb_mh_step_f32", "lslb_mh_step_f64", "lslb_spline_basis_f32",
     "lslb_spline_basis_f64",
 ]
 

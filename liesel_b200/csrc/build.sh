@@ -18,3 +18,9 @@ done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o libliesel_b200.so build/*.o -lcudart
 echo "built $(pwd)/libliesel_b200.so"
+# The jax.ffi shim, compiled against the TEST STUB of xla/ffi/api/ffi.h (jaxlib is not installable
+# here): keeps the shim compiling and lets tests/test_ffi_shim.py drive its handlers.
+g++ -shared -fPIC -std=c++17 -O1 -Wall -I ../../tests/stubs -I ../../include -I /usr/local/cuda/include \
+    xla_ffi_shim.cc -L. -lliesel_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$ORIGIN/..' \
+    -o build/liblslb_xla_ffi_stub.so
+echo "built $(pwd)/build/liblslb_xla_ffi_stub.so"

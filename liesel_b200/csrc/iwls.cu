@@ -658,9 +658,62 @@ template int launch_iwls<float>(const lslb_plan*, int, int, const float*, const 
 template int launch_iwls<double>(const lslb_plan*, int, int, const double*, const double*, double*,
                                  double*, double*, unsigned, void*, size_t, cudaStream_t);
 
+// ---------------------------------------------------------------------------------------
+// Metropolis-Hastings decision + state selection (reference goose/mh.py:48-68), one CTA per chain:
+//   log_acc = proposed - current + correction;  NaN -> (-inf, error code 90);
+//   acc = min(exp(log_acc), 1);  accept <=> u <= acc
+// and, fused, what the kernels do with the decision (iwls.py:337-342, mh.py:62-66): the accepted
+// proposal replaces the chain's row of `params` and its carried log-posterior.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+mh_step_kernel(int P, const T* __restrict__ u, T* __restrict__ cur_lp, const T* __restrict__ prop_lp,
+               const T* __restrict__ log_corr, T* __restrict__ params, const T* __restrict__ params_prop,
+               int* __restrict__ code, T* __restrict__ acc, unsigned char* __restrict__ moved) {
+  const int c = blockIdx.x;
+  T la = prop_lp[c] - cur_lp[c] + (log_corr ? log_corr[c] : T(0));
+  const bool nan = la != la;
+  if (nan) la = -INFINITY;
+  T a = exp(la);  // exp(-inf) = 0, exp(+inf) = inf
+  if (a > T(1)) a = T(1);
+  const bool accept = u[c] <= a;
+  __syncthreads();  // every thread has read cur_lp[c]
+  if (threadIdx.x == 0) {
+    if (code) code[c] = nan ? 90 : 0;
+    if (acc) acc[c] = a;
+    if (moved) moved[c] = accept ? 1 : 0;
+    if (accept) cur_lp[c] = prop_lp[c];
+  }
+  if (accept && params && params_prop) {
+    T* dst = params + (size_t)c * P;
+    const T* src = params_prop + (size_t)c * P;
+    for (int j = threadIdx.x; j < P; j += blockDim.x) dst[j] = src[j];
+  }
+}
+
+template <typename T>
+int launch_mh_step(int C, int P, const T* u, T* cur_lp, const T* prop_lp, const T* log_corr, T* params,
+                   const T* params_prop, int* code, T* acc, unsigned char* moved, cudaStream_t stream) {
+  if (C < 1 || P < 0 || !u || !cur_lp || !prop_lp) return LSLB_ERR_INVALID;
+  if ((params == nullptr) != (params_prop == nullptr)) return LSLB_ERR_INVALID;
+  mh_step_kernel<T><<<C, 128, 0, stream>>>(P, u, cur_lp, prop_lp, log_corr, params, params_prop, code, acc, moved);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
 }  // namespace lslb
 
 #define LSLB_S(x) ((cudaStream_t)(x))
+extern "C" int lslb_mh_step_f32(int C, int P, const float* u, float* cur_lp, const float* prop_lp,
+                                const float* log_corr, float* params, const float* params_prop, int* code,
+                                float* acc, unsigned char* moved, lslb_stream_t s) {
+  return lslb::launch_mh_step<float>(C, P, u, cur_lp, prop_lp, log_corr, params, params_prop, code, acc, moved, LSLB_S(s));
+}
+extern "C" int lslb_mh_step_f64(int C, int P, const double* u, double* cur_lp, const double* prop_lp,
+                                const double* log_corr, double* params, const double* params_prop, int* code,
+                                double* acc, unsigned char* moved, lslb_stream_t s) {
+  return lslb::launch_mh_step<double>(C, P, u, cur_lp, prop_lp, log_corr, params, params_prop, code, acc, moved, LSLB_S(s));
+}
 extern "C" int lslb_iwls_f32(const lslb_plan* plan, int C, int block, const float* params,
                              const float* aux, float* score, float* info, float* chol,
                              uint32_t flags, void* ws, size_t ws_bytes, lslb_stream_t s) {

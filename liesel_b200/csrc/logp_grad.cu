@@ -763,6 +763,17 @@ template int launch_logp_grad<double>(const lslb_plan*, int, const double*, cons
 
 }  // namespace lslb
 
+extern "C" const char* lslb_plan_kernel_name(const lslb_plan* plan, int C) {
+  using namespace lslb;
+  if (!plan || C < 1) return "";
+  if (dense_tc_eligible(plan, C)) return "lslb::dense_tc_k1 + lslb::dense_tc_k2";
+  if (dense_x2_eligible(plan)) return "lslb::dense_x2_kernel";
+  if (dgroup_x2_eligible(plan)) return "lslb::dgroup_x2_kernel";
+  if (banded_fast_eligible(plan))
+    return banded_cfg(plan, C).TC == 256 ? "lslb::banded_x2_kernel" : "lslb::banded_kernel";
+  return "lslb::eval_kernel";
+}
+
 extern "C" int lslb_logp_grad_f32(const lslb_plan* plan, int C, const float* params,
                                   const float* aux, float* logp, float* grad, uint32_t flags,
                                   void* ws, size_t ws_bytes, lslb_stream_t stream) {

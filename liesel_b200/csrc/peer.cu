@@ -10,6 +10,11 @@
 //    bitwise identical sum, with no library call and no host synchronisation on the path.
 //    Two slots alternate by epoch: a rank can only publish epoch e+2 after all peers signalled
 //    e+1, i.e. after they finished reading epoch e, so slot reuse needs no second barrier.
+//    A failure is fatal for the WHOLE group: a rank whose wait times out (or whose evaluation
+//    could not be launched) writes the poison value into its flag word on every peer; a rank that
+//    reads poison, or a flag two epochs ahead of its own (impossible in a healthy group), fails
+//    the same way. The error word is sticky: every later call of a failed rank publishes poison
+//    and returns NaN, until all ranks call lslb_peer_reset (a collective, bracketed by barriers).
 //  * NCCL (lslb_*_nccl_*): `ncclAllReduce(sum)` on the caller's communicator and stream, resolved
 //    from the process's libnccl.so.2 at first use (dlopen; the library is not a link dependency).
 //
@@ -33,6 +38,7 @@ struct lslb_peer {
   char* local;         // this rank's exchange buffer
   char* mapped[LSLB_MAX_PEERS];  // every rank's buffer as seen from here (mapped[rank] == local)
   bool connected;
+  bool poisoned;       // host mirror: a launch failed between peer_begin and peer_finish
 };
 
 namespace lslb {
@@ -40,6 +46,7 @@ namespace lslb {
 constexpr size_t PEER_FLAGS_OFF = 0;    // unsigned flags[W]: flags[r] = last epoch rank r published
 constexpr size_t PEER_ERR_OFF = 256;    // unsigned: set when a wait timed out
 constexpr size_t PEER_DATA_OFF = 512;
+constexpr unsigned PEER_POISON = 0xFFFFFFFFu;  // never a valid epoch
 
 struct PeerDev {
   const char* slot[LSLB_MAX_PEERS];  // slot of this epoch inside every rank's buffer
@@ -93,32 +100,40 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 peer_reduce_kernel(const __grid_constant__ PeerDev pd, T* __restrict__ out_a, size_t na,
                    T* __restrict__ out_b, size_t nb, size_t off_b, int vec_b) {
+  // a rank that failed before stays failed (sticky error word) and tells its peers so
+  __shared__ int failed;
+  if (threadIdx.x == 0) failed = *reinterpret_cast<volatile unsigned*>(pd.err) != 0u;
+  __syncthreads();
+  const bool dead = failed != 0;
   // publish: the partials were written by the preceding kernel on this stream
   if (blockIdx.x == 0 && (int)threadIdx.x < pd.world) {
     __threadfence_system();
-    st_release_sys(pd.flag_at[threadIdx.x], pd.epoch);
+    st_release_sys(pd.flag_at[threadIdx.x], dead ? PEER_POISON : pd.epoch);
   }
   // wait until every rank published this epoch. The wait is bounded (~10 s of SM clock): a rank that
-  // never arrives must not hang the GPU. A timed-out call is LOUD: the error flag is set and every
-  // output of this block becomes NaN (the reference's convention for a failed evaluation).
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  if ((int)threadIdx.x < pd.world) {
+  // never arrives must not hang the GPU. A failed call is LOUD and fatal for the group: the error
+  // flag is set, poison goes to every peer and every output of this block becomes NaN (the
+  // reference's convention for a failed evaluation).
+  if (!dead && (int)threadIdx.x < pd.world) {
     const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(pd.my_flags + threadIdx.x) - pd.epoch) < 0) {
-      if (clock64() - t0 > 20000000000LL) {
-        *pd.err = 1u;
-        timed_out = 1;
-        break;
-      }
+    for (;;) {
+      const unsigned f = ld_acquire_sys(pd.my_flags + threadIdx.x);
+      const int ahead = (int)(f - pd.epoch);
+      if (f == PEER_POISON || ahead >= 2) { failed = 1; break; }  // peer failed / slot already overwritten
+      if (ahead >= 0) break;
+      if (clock64() - t0 > 20000000000LL) { failed = 1; break; }
       __nanosleep(64);
     }
   }
   __syncthreads();
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nth = (size_t)gridDim.x * blockDim.x;
-  if (timed_out) {
+  if (failed) {
+    if (!dead && (int)threadIdx.x < pd.world) {
+      if (threadIdx.x == 0) *pd.err = 1u;
+      __threadfence_system();
+      st_release_sys(pd.flag_at[threadIdx.x], PEER_POISON);
+    }
     const T nan = (T)__int_as_float(0x7fc00000);
     for (size_t i = tid; i < na; i += nth) out_a[i] = nan;
     for (size_t i = tid; i < nb; i += nth) out_b[i] = nan;
@@ -133,12 +148,49 @@ peer_reduce_kernel(const __grid_constant__ PeerDev pd, T* __restrict__ out_a, si
   }
 }
 
+// Marks this rank failed and poisons its flag word on every peer (lslb_peer_abort and the error
+// returns between peer_begin and peer_finish).
+__global__ void peer_poison_kernel(const __grid_constant__ PeerDev pd) {
+  if ((int)threadIdx.x < pd.world) {
+    if (threadIdx.x == 0) *pd.err = 1u;
+    __threadfence_system();
+    st_release_sys(pd.flag_at[threadIdx.x], PEER_POISON);
+  }
+}
+
+static void fill_peer_dev(const lslb_peer* pr, unsigned e, PeerDev& pd) {
+  memset(&pd, 0, sizeof(pd));
+  for (int r = 0; r < pr->world; ++r) {
+    pd.slot[r] = pr->mapped[r] + PEER_DATA_OFF + (size_t)(e & 1u) * pr->slot_bytes;
+    pd.flag_at[r] = reinterpret_cast<unsigned*>(pr->mapped[r] + PEER_FLAGS_OFF) + pr->rank;
+  }
+  pd.my_flags = reinterpret_cast<unsigned*>(pr->local + PEER_FLAGS_OFF);
+  pd.err = reinterpret_cast<unsigned*>(pr->local + PEER_ERR_OFF);
+  pd.rank = pr->rank;
+  pd.world = pr->world;
+  pd.epoch = e;
+}
+
+static int peer_poison(lslb_peer* pr, cudaStream_t st) {
+  if (!pr || !pr->connected) return LSLB_ERR_INVALID;
+  pr->poisoned = true;
+  PeerDev pd;
+  fill_peer_dev(pr, pr->epoch, pd);
+  peer_poison_kernel<<<1, 32, 0, st>>>(pd);
+  LSLB_LAUNCH_CHECK();
+  return LSLB_OK;
+}
+
 static size_t region_b_offset(size_t na, size_t elem) { return (na * elem + 15) / 16 * 16; }
 
 // Pointers into the local slot of the NEXT epoch for the producing kernels.
 template <typename T>
 static int peer_begin(lslb_peer* pr, size_t na, size_t nb, cudaStream_t st, T** a, T** b) {
   if (!pr || !pr->connected) return LSLB_ERR_INVALID;
+  if (pr->poisoned) {
+    set_comm_error("peer group failed earlier (launch error or lslb_peer_abort); call lslb_peer_reset on all ranks");
+    return LSLB_ERR_COMM;
+  }
   if (region_b_offset(na, sizeof(T)) + nb * sizeof(T) > pr->slot_bytes) return LSLB_ERR_WORKSPACE;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   LSLB_CUDA(cudaStreamIsCapturing(st, &cs));
@@ -154,16 +206,7 @@ template <typename T>
 static int peer_finish(lslb_peer* pr, T* out_a, size_t na, T* out_b, size_t nb, cudaStream_t st) {
   const unsigned e = ++pr->epoch;
   PeerDev pd;
-  memset(&pd, 0, sizeof(pd));
-  for (int r = 0; r < pr->world; ++r) {
-    pd.slot[r] = pr->mapped[r] + PEER_DATA_OFF + (size_t)(e & 1u) * pr->slot_bytes;
-    pd.flag_at[r] = reinterpret_cast<unsigned*>(pr->mapped[r] + PEER_FLAGS_OFF) + pr->rank;
-  }
-  pd.my_flags = reinterpret_cast<unsigned*>(pr->local + PEER_FLAGS_OFF);
-  pd.err = reinterpret_cast<unsigned*>(pr->local + PEER_ERR_OFF);
-  pd.rank = pr->rank;
-  pd.world = pr->world;
-  pd.epoch = e;
+  fill_peer_dev(pr, e, pd);
   const size_t per = 16 / sizeof(T);
   const int vec_b = nb % per == 0 && reinterpret_cast<uintptr_t>(out_b) % 16 == 0;
   const size_t work = na + (vec_b ? nb / per : nb);
@@ -185,7 +228,10 @@ static int logp_grad_peer(const lslb_plan* plan, int C, const T* params, const T
   if (s != LSLB_OK) return s;
   if (pr->rank != 0) flags |= LSLB_SKIP_PRIOR;
   s = launch_logp_grad<T>(plan, C, params, aux, pa, grad ? pb : nullptr, flags, ws, ws_bytes, st);
-  if (s != LSLB_OK) return s;
+  if (s != LSLB_OK) {  // the peers are (or will be) waiting for this epoch: fail the group, do not desynchronise
+    peer_poison(pr, st);
+    return s;
+  }
   return peer_finish<T>(pr, logp, (size_t)C, grad, nb, st);
 }
 
@@ -201,7 +247,10 @@ static int iwls_peer(const lslb_plan* plan, int C, int block, const T* params, c
   if (s != LSLB_OK) return s;
   if (pr->rank != 0) flags |= LSLB_SKIP_PRIOR;
   s = launch_iwls<T>(plan, C, block, params, aux, pa, pb, nullptr, flags, ws, ws_bytes, st);
-  if (s != LSLB_OK) return s;
+  if (s != LSLB_OK) {
+    peer_poison(pr, st);
+    return s;
+  }
   s = peer_finish<T>(pr, score, na, info, nb, st);
   if (s != LSLB_OK || !chol) return s;
   return launch_chol<T>(C, (int)p, info, chol, st);
@@ -375,6 +424,18 @@ extern "C" int lslb_peer_timed_out(lslb_peer* pr, int* timed_out) {
   unsigned v = 0;
   LSLB_CUDA(cudaMemcpy(&v, pr->local + PEER_ERR_OFF, sizeof(v), cudaMemcpyDeviceToHost));
   *timed_out = (int)v;
+  return LSLB_OK;
+}
+
+extern "C" int lslb_peer_abort(lslb_peer* pr, lslb_stream_t s) { return peer_poison(pr, (cudaStream_t)s); }
+
+extern "C" int lslb_peer_reset(lslb_peer* pr) {
+  if (!pr || !pr->connected) return LSLB_ERR_INVALID;
+  LSLB_CUDA(cudaDeviceSynchronize());
+  LSLB_CUDA(cudaMemset(pr->local, 0, PEER_DATA_OFF));  // flag words and the error word
+  LSLB_CUDA(cudaDeviceSynchronize());
+  pr->epoch = 0;
+  pr->poisoned = false;
   return LSLB_OK;
 }
 

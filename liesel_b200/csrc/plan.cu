@@ -44,6 +44,31 @@ __global__ void span_changes_kernel(const int* __restrict__ start, long long n, 
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// out[0] = min, out[1] = max of an index array, out[2] = number of descents (one block, setup time)
+__global__ void index_range_kernel(const int* __restrict__ idx, long long n, int* out) {
+  __shared__ int lo[1024], hi[1024], dn[1024];
+  int a = 0x7fffffff, b = -0x7fffffff - 1, d = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int v = idx[i];
+    a = min(a, v);
+    b = max(b, v);
+    if (i > 0 && idx[i - 1] > v) ++d;
+  }
+  lo[threadIdx.x] = a;
+  hi[threadIdx.x] = b;
+  dn[threadIdx.x] = d;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      lo[threadIdx.x] = min(lo[threadIdx.x], lo[threadIdx.x + s]);
+      hi[threadIdx.x] = max(hi[threadIdx.x], hi[threadIdx.x + s]);
+      dn[threadIdx.x] += dn[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = lo[0]; out[1] = hi[0]; out[2] = dn[0]; }
+}
+
 // max_i |w_i0 + w_i1 + w_i2 + w_i3 - 1| over the rows of one spline block (one block, setup time)
 template <typename T>
 __global__ void unit_rows_kernel(const T* __restrict__ w, long long n, double* out) {
@@ -233,6 +258,35 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
       cudaFree(d_out);
     }
   }
+  // The kernels index coefficient storage with the caller's integers (spline: start .. start + 3,
+  // group: idx): validate their range once, here — an out-of-range value would be an out-of-bounds
+  // shared-/global-memory access in every later call. Group rows must also be ascending (the
+  // segment sums are deterministic because a group's rows are contiguous).
+  bool bad_index = false;
+  if (n > 0 && (p->ns > 0 || p->grp >= 0) && e == cudaSuccess) {
+    int* d_rng = nullptr;
+    e = cudaMalloc(&d_rng, sizeof(int) * 3 * (LSLB_MAX_SPL + 1));
+    if (e == cudaSuccess) {
+      int h[3 * (LSLB_MAX_SPL + 1)];
+      for (int m = 0; m < p->ns; ++m) index_range_kernel<<<1, 1024>>>(p->blk[p->sp[m]].index, n, d_rng + 3 * m);
+      if (p->grp >= 0) index_range_kernel<<<1, 1024>>>(p->blk[p->grp].index, n, d_rng + 3 * p->ns);
+      e = cudaMemcpy(h, d_rng, sizeof(int) * 3 * (p->ns + 1), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) {
+        for (int m = 0; m < p->ns; ++m)
+          if (h[3 * m] < 0 || h[3 * m + 1] > p->blk[p->sp[m]].ncoef - 4) bad_index = true;
+        if (p->grp >= 0) {
+          const int* g = h + 3 * p->ns;
+          if (g[0] < 0 || g[1] >= p->blk[p->grp].ncoef || g[2] != 0) bad_index = true;
+        }
+      }
+      cudaFree(d_rng);
+    }
+  }
+  if (bad_index) {
+    cudaFree(p->d_chunk_start);
+    delete p;
+    return LSLB_ERR_INVALID;
+  }
   // are the rows ordered for long constant-span runs?
   p->rows_sorted = p->ns > 0;
   if (p->ns > 0 && e == cudaSuccess) {
@@ -319,6 +373,10 @@ extern "C" void lslb_plan_destroy(lslb_plan* p) {
 
 extern "C" int lslb_plan_num_params(const lslb_plan* p) { return p ? p->P : -1; }
 extern "C" int lslb_plan_num_aux(const lslb_plan* p) { return p ? p->A : -1; }
+extern "C" int lslb_plan_dtype(const lslb_plan* p) { return p ? p->desc.dtype : -1; }
+extern "C" int lslb_plan_block_ncoef(const lslb_plan* p, int b) {
+  return (p && b >= 0 && b < p->desc.nblocks) ? p->blk[b].ncoef : -1;
+}
 extern "C" const char* lslb_plan_variant(const lslb_plan* p) { return p ? p->variant_name : ""; }
 extern "C" size_t lslb_workspace_bytes(const lslb_plan* p, int C) {
   return p ? lslb::workspace_bytes(p, C) : 0;

@@ -106,6 +106,21 @@ class PeerGroup:
             self._lib.check(self._lib.lib.lslb_peer_timed_out(self.handle, C.byref(flag)), "lslb_peer_timed_out")
         return bool(flag.value)
 
+    def abort(self):
+        """Fails the whole group: every rank's current or next sharded call returns NaN."""
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib.lslb_peer_abort(self.handle, self._lib.stream_ptr()), "lslb_peer_abort")
+
+    def reset(self, group=None):
+        """Collective recovery after a failure: barrier, clear every rank's flags and epoch, barrier."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group)
+            self._lib.check(self._lib.lib.lslb_peer_reset(self.handle), "lslb_peer_reset")
+            if self.world > 1:
+                dist.barrier(group)
+
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             with torch.cuda.device(self.device):

@@ -19,7 +19,7 @@ hands to the C ABI.
 
 from __future__ import annotations
 
-from typing import Callable, Sequence
+from typing import Callable, NamedTuple, Sequence
 
 import torch
 
@@ -27,6 +27,18 @@ from .plan import Plan
 
 Position = dict
 ModelState = dict
+
+
+class NodeState(NamedTuple):
+    """Same two fields as the reference's ``NodeState`` (``model/nodes.py:144-154``): code written
+    against a Liesel model state reads ``model_state[node_name].value``."""
+
+    value: object
+    outdated: bool = False
+
+
+def _val(entry):
+    return entry.value if isinstance(entry, NodeState) else entry
 
 
 class B200Interface:
@@ -57,16 +69,42 @@ class B200Interface:
         return cls(Plan(spec, device=device) if device is not None else Plan(spec))
 
     # -- ModelInterface protocol (types.py:72-102) ------------------------------------
+    # Two state layouts are understood. (1) Plain: ``{var_name: array}`` like ``DictInterface``.
+    # (2) Liesel-named (``liesel_state``): ``{node_name: NodeState(value, outdated)}`` keyed by the
+    # VALUE-NODE names of the reference's graph (``<var>_value``, ``model/nodes.py:2611-2613``), with
+    # positions keyed by variable names — what ``LieselInterface`` exposes
+    # (``goose/interface.py:267-302``, ``model/model.py`` ``extract_position``), so that code written
+    # against a Liesel model state (``tau2_gibbs_kernel``: ``group.value_from(model_state, "a")``,
+    # ``model/distreg.py:282-289``, ``model/nodes.py:3522-3545``) finds what it reads.
+    @staticmethod
+    def _resolve(key: str, model_state: ModelState) -> str | None:
+        if key in model_state:
+            return key
+        if key + "_value" in model_state:
+            return key + "_value"
+        return None
+
     def extract_position(self, position_keys: Sequence[str], model_state: ModelState) -> Position:
-        """Same contract as ``DictInterface.extract_position`` (``interface.py:75-88``)."""
-        return Position({key: model_state[key] for key in position_keys})
+        """Same contract as ``DictInterface.extract_position`` (``interface.py:75-88``); variable
+        names resolve to their value node in a Liesel-named state."""
+        out = Position()
+        for key in position_keys:
+            k = self._resolve(key, model_state)
+            if k is None:
+                raise KeyError(key)
+            out[key] = _val(model_state[k])
+        return out
 
     def update_state(self, position: Position, model_state: ModelState) -> ModelState:
         """``model_state | position`` (``interface.py:90-101``); evaluation is lazy."""
-        unknown = [k for k in position if k not in model_state]
+        unknown = [k for k in position if self._resolve(k, model_state) is None]
         if unknown:
             raise KeyError(f"unknown position keys {unknown}")
-        return model_state | position
+        new = dict(model_state)
+        for key, v in position.items():
+            k = self._resolve(key, model_state)
+            new[k] = NodeState(v, False) if isinstance(model_state[k], NodeState) else v
+        return new
 
     def log_prob(self, model_state: ModelState) -> torch.Tensor:
         """Unnormalised log-posterior per chain, ``[C]`` (``interface.py:304-313``)."""
@@ -118,12 +156,40 @@ class B200Interface:
             state[k] = v.expand(state[k].shape).contiguous() if v.dim() < state[k].dim() else v.contiguous()
         return state
 
+    def liesel_state(self, num_chains: int, position: dict | None = None) -> ModelState:
+        """
+        The start state under the reference's node names: ``<smooth>_beta_value``,
+        ``<smooth>_tau2_value`` plus the small constants an unmodified ``tau2_gibbs_kernel`` reads by
+        value-node name — ``<smooth>_a_value``, ``_b_value``, ``_rank_value``, ``_K_value``
+        (``model/distreg.py:155-161,282-289``) — every entry a ``NodeState``. The constants carry no
+        chain axis (under the engine's ``jax.vmap`` they are the per-chain scalars the kernel sees).
+        """
+        plain = self.initial_state(num_chains, position)
+        dev, dt = self.plan.device, self.plan.dtype
+        state: ModelState = {k + "_value": NodeState(v, False) for k, v in plain.items()}
+        for b in self.plan.spec.blocks:
+            if b.tau2_slot < 0:
+                continue
+            pr = b.prior
+            state[b.name + "_K_value"] = NodeState(torch.as_tensor(pr.K, dtype=dt, device=dev), False)
+            state[b.name + "_rank_value"] = NodeState(torch.tensor(float(pr.rank), dtype=dt, device=dev), False)
+            if pr.ig_a is not None:
+                state[b.name + "_a_value"] = NodeState(torch.tensor(float(pr.ig_a), dtype=dt, device=dev), False)
+                state[b.name + "_b_value"] = NodeState(torch.tensor(float(pr.ig_b), dtype=dt, device=dev), False)
+        return state
+
+    def _get(self, model_state: ModelState, key: str):
+        k = self._resolve(key, model_state)
+        if k is None:
+            raise KeyError(key)
+        return _val(model_state[k])
+
     def pack(self, model_state: ModelState):
         """State dict -> (params [C, P], aux [C, A]) in the plan's flat layout."""
-        params = torch.cat([model_state[k] for k in self._pos_keys], dim=1).contiguous()
+        params = torch.cat([self._get(model_state, k) for k in self._pos_keys], dim=1).contiguous()
         aux = None
         if self._aux_keys:
-            aux = torch.stack([model_state[k].reshape(-1) for k in self._aux_keys], dim=1).contiguous()
+            aux = torch.stack([self._get(model_state, k).reshape(-1) for k in self._aux_keys], dim=1).contiguous()
         return params, aux
 
     def unpack(self, params: torch.Tensor, aux: torch.Tensor | None = None) -> ModelState:

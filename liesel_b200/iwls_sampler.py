@@ -27,7 +27,7 @@ import math
 
 import torch
 
-from .plan import Plan, iwls_propose
+from .plan import Plan, iwls_propose, mh_step
 
 
 class IWLSGibbsSampler:
@@ -94,15 +94,12 @@ class IWLSGibbsSampler:
         lp_prop, _ = self.plan.logp_grad(params_prop, self.aux, want_grad=False)
         self.evals["iwls"] += 2
         self.evals["logp"] += 1
-        log_acc = lp_prop - self.logp + (bwd - fwd)
-        nan = torch.isnan(log_acc)
-        log_acc = torch.where(nan, torch.full_like(log_acc, -float("inf")), log_acc)  # mh.py:53-57
-        code = code + nan.to(torch.int32) * 90
-        acc = torch.exp(torch.clamp(log_acc, max=0.0))
         u = torch.rand(self.C, generator=self.gen, device=self.dev, dtype=self.dt)
-        accept = u <= acc
-        self.params = torch.where(accept[:, None], params_prop, self.params).contiguous()
-        self.logp = torch.where(accept, lp_prop, self.logp)
+        # mh_step (goose/mh.py:48-68: NaN -> -inf + code 90, acc = min(exp, 1), accept <=> u <= acc) and
+        # the selection of the accepted state, one launch
+        mh_code, acc, accept = mh_step(u, self.logp, lp_prop.contiguous(), (bwd - fwd).contiguous(),
+                                       self.params, params_prop)
+        code = code + mh_code
         if adapt_t is not None:
             self._da_step(blk.name, acc, adapt_t)
         return {"error_code": code, "acceptance_prob": acc, "position_moved": accept}

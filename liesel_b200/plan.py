@@ -31,6 +31,8 @@ class Plan:
         self.spec = spec
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda", torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = _TORCH[np.dtype(spec.dtype)]
         self._keep: list[torch.Tensor] = []
         self._ws: dict[int, torch.Tensor] = {}
@@ -89,12 +91,7 @@ class Plan:
                     d.index = rows[f"s{b}"].data_ptr()
                     if blk.center:
                         if blk.colmean is None:  # column means of the basis, accumulated in fp64
-                            w64 = rows[f"w{b}"].to(torch.float64)
-                            cols = rows[f"s{b}"].to(torch.int64)[:, None] + torch.arange(
-                                w64.shape[1], device=dev)[None, :]
-                            cm = torch.zeros(blk.ncoef, dtype=torch.float64, device=dev)
-                            cm.index_add_(0, cols.reshape(-1), w64.reshape(-1))
-                            blk.colmean = (cm / max(y.numel(), 1)).cpu().numpy().astype(spec.dtype)
+                            blk.colmean = self._column_means(rows, b, blk.ncoef).astype(spec.dtype)
                         cmt = torch.as_tensor(np.asarray(blk.colmean), device=dev).to(dt).contiguous()
                         self._keep.append(cmt)
                         d.center = cmt.data_ptr()
@@ -129,6 +126,25 @@ class Plan:
         self.n = int(y.numel())
         self.variant = _lib.lib.lslb_plan_variant(self._handle).decode()
         assert self.P == spec.num_params and self.A == spec.num_aux
+
+    @staticmethod
+    def _column_means(rows, b: int, ncoef: int) -> np.ndarray:
+        w64 = rows[f"w{b}"].to(torch.float64)
+        cols = rows[f"s{b}"].to(torch.int64)[:, None] + torch.arange(w64.shape[1], device=w64.device)[None, :]
+        cm = torch.zeros(ncoef, dtype=torch.float64, device=w64.device)
+        cm.index_add_(0, cols.reshape(-1), w64.reshape(-1))
+        return (cm / max(w64.shape[0], 1)).cpu().numpy()
+
+    def kernel_name(self, C_: int) -> str:
+        """Symbol of the row-streaming kernel a logp+grad call on ``C_`` chains launches (as ncu names it)."""
+        return _lib.lib.lslb_plan_kernel_name(self._handle, int(C_)).decode()
+
+    def column_means(self, block: int | str) -> np.ndarray:
+        """Column means (fp64) of a spline block's basis matrix, from the resident band."""
+        b = self.spec.block_index(block) if isinstance(block, str) else int(block)
+        if self.spec.blocks[b].kind != KIND_SPLINE:
+            raise ValueError("column_means is defined for spline blocks")
+        return self._column_means(self.rows, b, self.spec.blocks[b].ncoef)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -174,6 +190,14 @@ class Plan:
             grad = torch.empty((Cn, self.P), dtype=self.dtype, device=self.device) if want_grad else None
         else:
             logp, grad = out
+            if not want_grad:
+                grad = None
+            _lib.require_cuda(logp, grad)
+            for name, t, shape in (("logp", logp, (Cn,)), ("grad", grad, (Cn, self.P))):
+                if t is not None and (t.dtype != self.dtype or t.device != self.device or tuple(t.shape) != shape):
+                    raise _lib.LieselB200Error(f"out {name} must be a contiguous {shape} {self.dtype} tensor on {self.device}")
+            if want_grad and grad is None:
+                raise _lib.LieselB200Error("want_grad=True needs a grad output tensor")
         ws = self.workspace(Cn)
         with torch.cuda.device(self.device):
             if shard is None:
@@ -250,3 +274,23 @@ def iwls_propose(beta, score, chol_, step, z=None, x_eval=None):
                       _lib.ptr(z), _lib.ptr(x_eval), _lib.ptr(prop), _lib.ptr(logq),
                       _lib.stream_ptr()), "lslb_iwls_propose")
     return prop, logq
+
+
+def mh_step(u, cur_lp, prop_lp, log_corr=None, params=None, params_prop=None):
+    """
+    Metropolis-Hastings step of the reference (``goose/mh.py:48-68``) for all chains in one launch:
+    returns (error_code int32 [C], acceptance_prob [C], moved bool [C]); ``cur_lp`` and (when given)
+    ``params`` are updated IN PLACE where the proposal is accepted.
+    """
+    _lib.require_cuda(u, cur_lp, prop_lp, log_corr, params, params_prop)
+    Cn = u.shape[0]
+    P = 0 if params is None else params.shape[1]
+    code = torch.empty(Cn, dtype=torch.int32, device=u.device)
+    acc = torch.empty_like(u)
+    moved = torch.empty(Cn, dtype=torch.uint8, device=u.device)
+    with torch.cuda.device(u.device):
+        fn = getattr(_lib.lib, "lslb_mh_step_" + _lib.sfx(u.dtype))
+        _lib.check(fn(Cn, P, _lib.ptr(u), _lib.ptr(cur_lp), _lib.ptr(prop_lp), _lib.ptr(log_corr),
+                      _lib.ptr(params), _lib.ptr(params_prop), _lib.ptr(code), _lib.ptr(acc),
+                      _lib.ptr(moved), _lib.stream_ptr()), "lslb_mh_step")
+    return code, acc, moved.bool()

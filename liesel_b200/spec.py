@@ -221,8 +221,12 @@ class ModelSpec:
         """
         pred = self._check_predictor(predictor)
         self._check_name(name)
+        if order != 3:
+            raise ValueError(f"only cubic B-splines (order=3) are implemented on the device, got order={order}")
         knots = np.sort(np.asarray(knots, dtype=self.dtype))  # splines.py:183
         k = knots.shape[0] - order - 1
+        if k < order + 1:
+            raise ValueError("too few knots for a cubic basis")
         x = None if x is None else np.ascontiguousarray(np.asarray(x), dtype=self.dtype)
         if x is not None and x.shape != (self.n,):
             raise ValueError("x must be a 1d array with one entry per observation")
@@ -237,8 +241,14 @@ class ModelSpec:
         else:
             blk.center = bool(center)
         if start is not None:
+            if weights is None:
+                raise ValueError("a precomputed band needs both start and weights")
             blk.start = np.ascontiguousarray(start, dtype=np.int32)
             blk.weights = np.ascontiguousarray(weights, dtype=self.dtype)
+            if blk.start.shape != (self.n,) or blk.weights.shape != (self.n, order + 1):
+                raise ValueError(f"band must be start [n] and weights [n, {order + 1}]")
+            if self.n and (blk.start.min() < 0 or blk.start.max() > k - (order + 1)):
+                raise ValueError(f"band start out of range: need 0 <= start <= {k - (order + 1)}")
         self.blocks.append(blk)
         return self._relayout()
 

@@ -90,3 +90,31 @@ class CpuPort:
             self.logp_grad(params, aux)
             best.append(time.perf_counter() - t0)
         return float(np.median(best))
+
+
+class CpuEvaluator:
+    """Duck-typed evaluator for ``liesel_b200.nuts_gibbs.NutsGibbs`` on the CPU port (the CPU arm of
+    the ESS measurement in ``bench.py`` and the CPU tests of the sampler wiring)."""
+
+    def __init__(self, spec, threads: int | None = None):
+        self.port = CpuPort(spec, threads)
+        self.device, self.dtype = torch.device("cpu"), torch.float32
+        self._K = {b.name: torch.from_numpy(np.asarray(b.prior.K, dtype=np.float64))
+                   for b in spec.blocks if b.prior is not None and hasattr(b.prior, "K")}
+        self._sl = {b.name: slice(b.param_offset, b.param_offset + b.ncoef) for b in spec.blocks}
+
+    def logp_grad(self, q, aux, out=None):
+        lp, g = self.port.logp_grad(q.numpy(), aux.numpy())
+        if out is not None:
+            out[0].copy_(lp)
+            out[1].copy_(g)
+            return out
+        return lp, g
+
+    def quadform(self, name, q):
+        b = q[:, self._sl[name]].double()
+        return ((b @ self._K[name]) * b).sum(dim=1)
+
+    def column_means(self, spec) -> dict:
+        """Column means of every spline block's DENSE basis (what ``Plan.column_means`` returns)."""
+        return {blk.name: X.double().mean(dim=0).numpy() for blk, X in self.port.designs if blk.kind == sam.KIND_SPLINE}

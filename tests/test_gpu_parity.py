@@ -855,3 +855,165 @@ def test_hmc_on_device(lb):
     acc = float(torch.stack([i.acceptance_prob for i in infos]).mean())
     assert 0.6 < acc < 0.97
     assert torch.isfinite(draws).all()
+
+
+# --- BASELINE-size parity of configs 2 and 3 ---------------------------------------------------------
+def test_full_size_iwls_s3_all_blocks(lb):
+    """BASELINE config 3 at size: the IWLS pass (score, observed information, ridge + Cholesky) of all
+    four blocks of the Gaussian location-scale model at n = 1e6 with 256 chains on the device, three of
+    them against the fp64 oracle. Same tolerance formula as the n = 5e4 cases — the information
+    entries are fp32 sums over up to n/148 rows per accumulator, which small-n parity cannot vouch for."""
+    spec, centre = synth.s3_gamlss(n=1_000_000)
+    plan = lb.Plan(spec)
+    assert plan.variant == "banded_tma_runlength"
+    th, aux = synth.evaluation_points(spec, centre, 256, tau2="loguniform")
+    for name in ["loc_p0", "loc_np0", "scale_p0", "scale_np0"]:
+        check_iwls(spec, plan, name, th, aux, chains=[0, 101, 255])
+
+
+def test_full_size_s2_against_oracle(lb):
+    """BASELINE config 2 at size (n = 1e5, 5 centred cubic P-splines, 64 chains): log-posterior,
+    gradient and one block's IWLS pass against the fp64 oracle."""
+    spec, centre = synth.s2_pspline_gam(n=100_000)
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 64, tau2="loguniform")
+    check_logp_grad(spec, plan, th, aux, chains=[0, 31, 63])
+    check_iwls(spec, plan, "loc_np3", th, aux, chains=[0, 63])
+
+
+# --- Metropolis-Hastings step (goose/mh.py) ------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mh_step_decisions_match_the_reference_rule(dtype):
+    """``lslb_mh_step`` against ``oracle.iwls.mh_step`` (reference goose/mh.py:48-68) on crafted
+    inputs: NaN acceptance (code 90, never accepted unless u == 0), +/-inf log-probabilities, the
+    inf - inf = NaN case, ties ``u == acc`` (accepted: the rule is ``<=``), exp overflow clipped to 1."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from liesel_b200.plan import mh_step
+
+    inf, nan = np.inf, np.nan
+    cur = np.array([-10.0, -10.0, -10.0, -inf, -inf, -10.0, nan, -10.0, -10.0, 5.0, -1e30, -10.0, -3.0, -3.0], dtype=dtype)
+    prop = np.array([-9.0, -11.0, nan, -5.0, -inf, -inf, -4.0, inf, -10.0, 5.0, 1e30, -10.5, -3.0, -4.0], dtype=dtype)
+    corr = np.array([0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, nan, 0.0, 0.0, 0.0, -0.0, 1.0], dtype=dtype)
+    u = np.array([0.999, 0.2, 0.0, 0.5, 0.5, 0.0, 0.3, 1.0, 0.1, 1.0, 0.7, 0.0, 1.0, 1.0], dtype=dtype)
+    with np.errstate(invalid="ignore"):
+        acc_exact = np.minimum(np.exp((prop - cur + corr).astype(dtype)), 1)
+    u[11] = acc_exact[11]  # tie at an interior acceptance probability: u == exp(-0.5)
+    C, P = cur.shape[0], 7
+    rng = np.random.default_rng(0)
+    p_cur, p_prop = rng.normal(size=(C, P)).astype(dtype), rng.normal(size=(C, P)).astype(dtype)
+    with np.errstate(invalid="ignore"):
+        r_code, r_acc, r_accept = OI.mh_step(u, cur, prop, corr)
+    d = lambda a: torch.as_tensor(a.copy(), device="cuda")
+    d_cur, d_par = d(cur), d(p_cur)
+    code, acc, moved = mh_step(d(u), d_cur, d(prop), d(corr), d_par, d(p_prop))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(code.cpu().numpy(), r_code)
+    np.testing.assert_allclose(acc.cpu().numpy(), r_acc.astype(dtype), rtol=4e-7 if dtype == np.float32 else 1e-15)
+    got = moved.cpu().numpy()
+    # the interior tie depends on the last bit of exp(): everything else must agree exactly
+    keep = np.arange(C) != 11
+    np.testing.assert_array_equal(got[keep], r_accept[keep])
+    assert got[11] == (u[11] <= acc.cpu().numpy()[11])
+    assert r_code[2] == 90 and r_accept[2] and r_code[4] == 90 and not r_accept[4] and r_accept[5]  # the crafted cases
+    # state selection: accepted rows take the proposal (and its log-prob), the others stay
+    want_par = np.where(got[:, None], p_prop, p_cur)
+    np.testing.assert_array_equal(d_par.cpu().numpy(), want_par)
+    np.testing.assert_array_equal(d_cur.cpu().numpy(), np.where(got, prop, cur))
+
+
+# --- the reference's kernel recovery pin on the device (tests/goose/kernels/model_lm.py:70-84) -----------
+def _model_lm_plan(lb, golden_dir):
+    import json
+    import os
+
+    from liesel_b200.spec import ModelSpec
+
+    g = json.load(open(os.path.join(golden_dir, "model_lm.json")))
+    X, y = np.array(g["X"]), np.array(g["y"])
+    spec = ModelSpec(dtype=np.dtype(np.float64))
+    spec.add_response(y, "normal").add_predictor("loc").add_predictor("scale")
+    spec.add_p_smooth(X, 0.0, None, "loc", "beta")
+    spec.add_p_smooth(np.ones((30, 1)), 0.0, None, "scale", "log_sigma")
+    return g, lb.Plan(spec)
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_nuts_on_device_recovers_model_lm(lb, golden_dir, compact):
+    """``tests/goose/kernels/test_nuts.py`` through ``model_lm.py:70-84`` with everything on the GPU:
+    CUDA log-prob/gradient through the C ABI, the fused leaf kernels (``lslb_nuts_leaf_pre/post``),
+    with and without dropping finished chains. The reference's three bounds: posterior mean of beta
+    within 5 % of OLS, mean log sigma within 5 % of log sigma_OLS, mean acceptance within 0.05 of the
+    dual-averaging target 0.8 (long final fast epoch as in ``model_lm.py:56-60``)."""
+    from liesel_b200.nuts import BatchedNUTS
+
+    g, plan = _model_lm_plan(lb, golden_dir)
+    C = 64
+    q0 = torch.tensor([g["beta"] + [g["log_sigma"]]], dtype=torch.float64, device="cuda").repeat(C, 1)
+
+    def f_into(q, lp, gr, chains=None):
+        plan.logp_grad(q, None, out=(lp, gr))
+
+    s = BatchedNUTS(lambda q: plan.logp_grad(q.contiguous(), None), q0, seed=42, logp_grad_into=f_into,
+                    compact=compact)
+    assert s.fused and s.compact == compact
+    s.warmup(2000, term_duration=1500)
+    draws, infos = s.sample(400)
+    d = draws.cpu().numpy()
+    assert d[:, :, :2].mean(axis=(0, 1)) == pytest.approx(np.array(g["beta_ols"]), rel=0.05)
+    assert d[:, :, 2].mean() == pytest.approx(np.log(g["sigma_ols"]), rel=0.05)
+    acc = np.mean([float(i.acceptance_prob.mean()) for i in infos])
+    assert acc == pytest.approx(0.8, abs=0.05), acc
+    codes = torch.cat([i.error_code for i in infos])
+    assert float((codes == 0).float().mean()) > 0.98
+    from liesel_b200 import diagnostics
+
+    assert diagnostics.split_rhat_device(draws).max() < 1.02
+
+
+def test_hmc_on_device_recovers_model_lm(lb, golden_dir):
+    """``tests/goose/kernels/test_hmc.py`` through ``model_lm.py:70-84`` on the device (same bounds)."""
+    from liesel_b200.nuts import BatchedHMC
+
+    g, plan = _model_lm_plan(lb, golden_dir)
+    C = 64
+    q0 = torch.tensor([g["beta"] + [g["log_sigma"]]], dtype=torch.float64, device="cuda").repeat(C, 1)
+    s = BatchedHMC(lambda q: plan.logp_grad(q.contiguous(), None), q0, seed=7)
+    s.warmup(2000, term_duration=1500)
+    draws, infos = s.sample(600)
+    d = draws.cpu().numpy()
+    assert d[:, :, :2].mean(axis=(0, 1)) == pytest.approx(np.array(g["beta_ols"]), rel=0.05)
+    assert d[:, :, 2].mean() == pytest.approx(np.log(g["sigma_ols"]), rel=0.05)
+    acc = np.mean([float(i.acceptance_prob.mean()) for i in infos])
+    assert acc == pytest.approx(0.8, abs=0.05), acc
+
+
+def test_nuts_gibbs_on_device_converges(lb):
+    """The sampling scheme of the ESS metric (one NUTS block + Gibbs tau2, sum-to-zero constraint) on
+    the device at a reduced H: chains agree (rank-normalised split-R-hat), no divergences, the
+    constrained fit reproduces the data-generating curves."""
+    from liesel_b200 import reparam
+    from liesel_b200.nuts_gibbs import NutsGibbs, PlanEvaluator, summarise
+
+    spec, centre = synth.s3_gamlss(n=50_000)
+    plan = lb.Plan(spec)
+    cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
+    rep = reparam.sum_to_zero(spec, cm, device=plan.device)
+    C = 256
+    th, aux = synth.evaluation_points(spec, centre, C, seed=1)
+    run = NutsGibbs(spec, PlanEvaluator(plan), dev(th, plan), dev(aux, plan), reparam=rep, seed=1, compact=True)
+    run.warmup(300)
+    draws, infos = run.sample(200)
+    s = summarise(draws, infos, 1.0)
+    assert s["split_rhat_max"] < 1.02, s
+    assert s["ess_bulk_min"] > 0.3 * C * 200, s
+    assert s["divergent_frac"] < 0.01 and s["mean_treedepth"] < 7, s
+    # fitted mean curve: eta_loc = beta0 + B beta (uncentred basis, full coordinates) ~ 1 + sin(2 pi x)
+    q = run.full(draws.reshape(-1, draws.shape[2])).double().mean(dim=0).cpu().numpy()
+    from oracle import splines as OSp
+
+    xs = np.linspace(0.05, 0.95, 19)
+    blk = spec.block("loc_np0")
+    B = OSp.basis_matrix(xs, np.asarray(blk.knots, dtype=np.float64), 3)
+    fit = q[0] + B @ q[blk.param_offset: blk.param_offset + blk.ncoef]
+    np.testing.assert_allclose(fit, 1.0 + np.sin(2 * np.pi * xs), atol=0.05)

@@ -138,3 +138,59 @@ def test_interface_protocol_mirrors_dict_interface_semantics():
         iface.extract_position(["not_a_variable"], state0)
     with pytest.raises(KeyError):
         iface.chol_info_fn("not_a_variable")
+
+
+def test_liesel_named_state_serves_an_unmodified_tau2_gibbs_kernel():
+    """The reference's ``tau2_gibbs_kernel`` (model/distreg.py:277-297) reads ``a``, ``rank``, ``b``,
+    ``beta`` and ``K`` out of the model state through ``Group.value_from`` — i.e.
+    ``model_state[<value node name>].value`` (model/nodes.py:3522-3545) — and returns
+    ``{<tau2 var name>: draw}``. ``B200Interface.liesel_state`` carries exactly those entries, and
+    ``update_state`` / ``extract_position`` accept the variable-name keys the kernel and the engine
+    use. The transition below is the reference's, with torch in place of jnp/jax.random and the
+    group replaced by its name table (what ``Group.__getitem__`` + ``Var.value_node.name`` give)."""
+    import torch
+    from types import SimpleNamespace
+
+    from liesel_b200.interface import B200Interface, NodeState
+
+    spec, _ = synth.s3_gamlss(n=50)
+    iface = B200Interface(SimpleNamespace(spec=spec, device=torch.device("cpu"), dtype=torch.float32))
+    state = iface.liesel_state(1, {"loc_np0_beta": torch.linspace(-1, 1, 20)[None, :]})
+    assert all(isinstance(v, NodeState) for v in state.values())
+
+    name = "loc_np0"
+    members = {m: f"{name}_{m}_value" for m in ("a", "b", "rank", "K", "beta", "tau2")}  # value node names
+
+    def value_from(model_state, member):  # Group.value_from
+        return model_state[members[member]].value
+
+    position_key = name + "_tau2"  # group["tau2"].name
+
+    def transition(gen, model_state):  # distreg.py:281-295, per chain (the engine vmaps it)
+        a_prior = value_from(model_state, "a")
+        rank = value_from(model_state, "rank")
+        a_gibbs = torch.squeeze(a_prior + 0.5 * rank)
+        b_prior = value_from(model_state, "b")
+        beta = value_from(model_state, "beta")[0]
+        K = value_from(model_state, "K")
+        b_gibbs = torch.squeeze(b_prior + 0.5 * (beta @ K @ beta))
+        draw = b_gibbs / torch._standard_gamma(a_gibbs.reshape(1), generator=gen)
+        return {position_key: draw}
+
+    gen = torch.Generator().manual_seed(3)
+    pos = transition(gen, state)
+    beta = torch.linspace(-1, 1, 20).double()
+    K = torch.as_tensor(spec.block(name).prior.K)
+    # the full conditional's parameters are the closed form a + rank/2, b + beta'K beta/2
+    assert float(state[members["a"]].value + 0.5 * state[members["rank"]].value) == 1.0 + 9.0
+    np.testing.assert_allclose(float(state[members["b"]].value) + 0.5 * float(beta @ K @ beta),
+                               0.005 + 0.5 * float(beta @ K @ beta), rtol=1e-6)
+    state2 = iface.update_state(pos, state)  # the engine applies the Gibbs draw by VARIABLE name
+    assert isinstance(state2[members["tau2"]], NodeState)
+    assert state2[members["tau2"]].value is pos[position_key]
+    assert state[members["tau2"]].value is not pos[position_key]  # purity
+    got = iface.extract_position([position_key, name + "_beta"], state2)
+    assert got[position_key] is pos[position_key]
+    params, aux = iface.pack(state2)
+    assert params.shape == (1, 42) and aux.shape == (1, 2)
+    assert float(aux[0, 0]) == float(pos[position_key])

@@ -62,6 +62,38 @@ def test_sharded_entry_points_world1():
         h.close()
 
 
+def test_peer_group_failure_is_loud_and_recoverable():
+    """A failed peer group never returns a partial sum: after ``abort`` (what a timed-out wait or a
+    failed launch does) the host refuses further calls with a status code, the device-side error
+    word is set, and ``reset`` brings the group back to bitwise identical results."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from liesel_b200 import _lib
+    from liesel_b200 import dist as ld
+    from liesel_b200.plan import Plan
+
+    spec, centre = synth.s3_gamlss(n=20_000)
+    plan = Plan(spec)
+    C = 40
+    th, aux = synth.evaluation_points(spec, centre, C)
+    t, ax = torch.as_tensor(th, device=plan.device), torch.as_tensor(aux, device=plan.device)
+    lp0, g0 = plan.logp_grad(t, ax)
+    peer = ld.PeerGroup(C * 43, plan.device)
+    lp, g = plan.logp_grad(t, ax, shard=peer)
+    assert torch.equal(lp, lp0) and not peer.timed_out()
+    peer.abort()
+    torch.cuda.synchronize()
+    assert peer.timed_out()
+    with pytest.raises(_lib.LieselB200Error):
+        plan.logp_grad(t, ax, shard=peer)
+    peer.reset()
+    assert not peer.timed_out()
+    for _ in range(3):
+        lp, g = plan.logp_grad(t, ax, shard=peer)
+        assert torch.equal(lp, lp0) and torch.equal(g, g0)
+    peer.close()
+
+
 def test_row_sharded_two_gpus():
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs on one box")

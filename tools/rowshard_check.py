@@ -128,6 +128,23 @@ def check_model(tag, spec, centre, C, iwls_block=None, rtol=2e-5):
         ok_seq = ok_seq and torch.equal(lp, torch_sum(l2)) and torch.equal(g, torch_sum(g2))
     res["peer_sequence"] = bool(ok_seq)
     res["peer_timed_out"] = peer.timed_out()
+    if world > 1 and iwls_block is not None and spec.dtype == np.float32:
+        # failure is fatal for the whole group: the LAST rank aborts instead of evaluating; every
+        # other rank's call must come back all-NaN with its error word set (never a partial sum),
+        # and a collective reset restores bitwise identical results
+        if rank == world - 1:
+            peer.abort()
+            torch.cuda.synchronize()
+            saw = peer.timed_out()
+        else:
+            lp, g = part.logp_grad(t, ax, shard=peer)
+            torch.cuda.synchronize()
+            saw = bool(torch.isnan(lp).all() and torch.isnan(g).all()) and peer.timed_out()
+        peer.reset()
+        lp, g = part.logp_grad(t, ax, shard=peer)
+        torch.cuda.synchronize()
+        res["peer_poison_then_reset"] = bool(saw and not peer.timed_out() and torch.equal(lp, lp_sum)
+                                             and torch.equal(g, g_sum))
     res["variant"] = part.variant
     peer.close()
     nccl.close()
