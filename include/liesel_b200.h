@@ -223,6 +223,16 @@ int lslb_spline_basis_f32(const float* x, int64_t n, const float* knots, int nkn
                           int32_t* start, float* weights, lslb_stream_t stream);
 int lslb_spline_basis_f64(const double* x, int64_t n, const double* knots, int nknots,
                           int32_t* start, double* weights, lslb_stream_t stream);
+/*
+ * Any order 0..3 of the same recursion (contrib/splines.py:109-198 is order-generic). The band
+ * stays FOUR wide, the layout every evaluation kernel streams: the order + 1 weights that can be
+ * non-zero lie inside [start, start + 3], start = clip(span - order, 0, k - 4) with
+ * k = nknots - order - 1 >= 4 basis functions; the other entries of the window are exact zeros.
+ */
+int lslb_spline_basis_order_f32(const float* x, int64_t n, const float* knots, int nknots, int order,
+                                int32_t* start, float* weights, lslb_stream_t stream);
+int lslb_spline_basis_order_f64(const double* x, int64_t n, const double* knots, int nknots, int order,
+                                int32_t* start, double* weights, lslb_stream_t stream);
 
 /*
  * Row sharding over the GPUs of one box (no counterpart in the reference, which has no

@@ -95,6 +95,9 @@ for _sfx in ("f32", "f64"):
     f = getattr(lib, "lslb_spline_basis_" + _sfx)
     f.restype = _i
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
+    f = getattr(lib, "lslb_spline_basis_order_" + _sfx)
+    f.restype = _i
+    f.argtypes = [_vp, _i64, _vp, _i, _i, _vp, _vp, _vp]
 
 for _sfx in ("f32", "f64"):
     # row-sharded variants: one more pointer (lslb_peer* / ncclComm_t) before the stream
@@ -156,7 +159,7 @@ EXPORTS = [
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",
     "lslb_iwls_f64", "lslb_chol_f32", "lslb_chol_f64", "lslb_quadform_f32", "lslb_quadform_f64",
     "lslb_iwls_propose_f32", "lslb_iwls_propose_f64", "lslb_mh_step_f32", "lslb_mh_step_f64", "lslb_spline_basis_f32",
-    "lslb_spline_basis_f64",
+    "lslb_spline_basis_f64", "lslb_spline_basis_order_f32", "lslb_spline_basis_order_f64",
 ]
 
 
@@ -196,8 +199,9 @@ def require_cuda(*tensors: torch.Tensor) -> None:
             raise LieselB200Error("tensors passed to the C ABI must be contiguous")
 
 
-def spline_basis(x: torch.Tensor, knots: torch.Tensor):
-    """Banded cubic basis on the device: (start int32 [n], weights [n, 4])."""
+def spline_basis(x: torch.Tensor, knots: torch.Tensor, order: int = 3):
+    """Banded B-spline basis of order 0..3 on the device: (start int32 [n], weights [n, 4]); for
+    order < 3 the window is zero-padded (see ``lslb_spline_basis_order_*``)."""
     require_cuda(x, knots)
     if x.dtype != knots.dtype:
         raise TypeError("x and knots must share a dtype")
@@ -205,7 +209,7 @@ def spline_basis(x: torch.Tensor, knots: torch.Tensor):
     start = torch.empty(n, dtype=torch.int32, device=x.device)
     w = torch.empty((n, 4), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        fn = getattr(lib, "lslb_spline_basis_" + sfx(x.dtype))
-        check(fn(ptr(x), n, ptr(knots), knots.numel(), ptr(start), ptr(w), stream_ptr()),
-              "lslb_spline_basis")
+        fn = getattr(lib, "lslb_spline_basis_order_" + sfx(x.dtype))
+        check(fn(ptr(x), n, ptr(knots), knots.numel(), int(order), ptr(start), ptr(w), stream_ptr()),
+              "lslb_spline_basis_order")
     return start, w

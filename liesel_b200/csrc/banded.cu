@@ -302,8 +302,18 @@ bool banded_fast_eligible(const lslb_plan* plan) {
   return true;
 }
 
-// float32 with more than 128 chains: two chains per thread, packed f32x2 math (banded_x2.cu)
-static bool use_x2(const lslb_plan* plan, int C) { return plan->desc.dtype == LSLB_F32 && C > 128; }
+// float32 with more than 32 chains: two chains per thread, packed f32x2 math (banded_x2.cu). Below
+// that a warp of chain pairs would be at most half full and the scalar kernel (thread = chain) runs.
+// (Until round 2 the threshold was 128 chains: strong-scaling the headline's 1024 chains over 8 GPUs,
+// or a NUTS batch compacted to its last running chains, fell back to the scalar kernel at 2.5x the
+// pro-rata time; LSLB_X2_MIN_CHAINS restores any threshold for A/B runs.)
+static bool use_x2(const lslb_plan* plan, int C) {
+  static const int min_chains = [] {
+    const char* e = getenv("LSLB_X2_MIN_CHAINS");
+    return e ? atoi(e) : 33;
+  }();
+  return plan->desc.dtype == LSLB_F32 && C >= min_chains;
+}
 
 BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   BandedCfg k;
@@ -324,7 +334,7 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
   int ctas_per_sm = x2 ? 16 / (k.tc_eff / 64) : 6;  // x2: at most 16 resident warps per SM (registers)
-  if (ctas_per_sm > 5) ctas_per_sm = 5;             // shared memory: 34 KB of row stages per CTA
+  if (ctas_per_sm > (x2 ? 6 : 5)) ctas_per_sm = x2 ? 6 : 5;  // shared memory: 34 KB of row stages per CTA
   static const int knob_ctas = [] {  // tuning knob, read once
     const char* e = getenv("LSLB_BANDED_CTAS_PER_SM");
     return e ? atoi(e) : 0;

@@ -4,9 +4,12 @@
 // Why packed: a packed instruction does two chains' worth of FP32 work per issue slot, which frees
 // issue bandwidth for the shared-memory broadcasts and MUFU ops that accompany the 16 FMAs of a row.
 //
-// Data flow per CTA (128 threads = 256 chains, one row chunk):
-//   TMA bulk copies (the caller's SoA arrays, 128-row tiles, 3-stage ring, mbarrier complete_tx)
-//   -> all warps run the row loop on the tile with shared-memory broadcasts. A row's weights are
+// Data flow per CTA (up to 512 threads = 16 warps = 1024 chains; ONE CTA per SM, or several smaller
+// ones when the chain count is low; each CTA owns one chunk of rows):
+//   TMA bulk copies (the caller's SoA arrays, 128-row tiles, LSLB_X2_STAGES = 6-stage ring, mbarrier
+//   complete_tx) -> all warps run the row loop on the tile with shared-memory broadcasts. The warps
+//   are NOT synchronised per tile: a shared counter per stage lets the last warp that leaves a stage
+//   refill it, so warps drift up to 6 tiles apart and nobody waits at a barrier. A row's weights are
 //   scalars shared by both chains of a thread: FFMA2 takes them as a 32-bit operand broadcast to
 //   both halves (SASS `Rn.F32`), so nothing is duplicated in shared memory and the register file
 //   reads one register instead of a pair.

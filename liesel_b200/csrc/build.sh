@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
        -I ../../include -Xptxas -v --expt-relaxed-constexpr ${NVCC_EXTRA:-})
-SRCS=(plan.cu logp_grad.cu iwls.cu spline_basis.cu debug.cu banded.cu banded_x2.cu dense_x2.cu banded_iwls_x2.cu dgroup_x2.cu nuts.cu tc_probe.cu dense_tc.cu peer.cu)
+SRCS=(plan.cu logp_grad.cu iwls.cu spline_basis.cu debug.cu banded.cu banded_x2.cu dense_x2.cu banded_iwls_x2.cu dgroup_x2.cu msmooth_x2.cu nuts.cu tc_probe.cu dense_tc.cu peer.cu)
 mkdir -p build
 pids=()
 for s in "${SRCS[@]}"; do

@@ -278,6 +278,10 @@ bool dense_x2_eligible(const lslb_plan* plan);  // dense_x2.cu
 BandedCfg dense_x2_cfg(const lslb_plan* plan, int C);
 int launch_dense_x2(const lslb_plan* plan, const EvalParams<float>& ep, const BandedCfg& k,
                     bool want_grad, cudaStream_t st);
+bool msmooth_x2_eligible(const lslb_plan* plan);  // msmooth_x2.cu
+LaunchCfg msmooth_x2_cfg(const lslb_plan* plan, int C);
+int launch_msmooth_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k,
+                      bool want_grad, cudaStream_t st);
 bool banded_fast_eligible(const lslb_plan* plan);  // banded.cu
 BandedCfg banded_cfg(const lslb_plan* plan, int C);
 template <typename T>

@@ -334,7 +334,8 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   // kernel variant
   if (p->grp < 0 && p->nd == 0 && p->ns >= 1) {
     p->variant = VAR_BANDED;
-    p->variant_name = banded_fast_eligible(p) ? "banded_tma_runlength" : "banded_runlength";
+    p->variant_name = banded_fast_eligible(p) ? "banded_tma_runlength"
+                      : (msmooth_x2_eligible(p) ? "multi_smooth_x2" : "banded_runlength");
   } else if (p->ns == 0 && p->nd == 1 && p->blk[p->dn[0]].ncoef <= 16) {
     p->variant = VAR_DENSE_REG;
     p->variant_name = dgroup_x2_eligible(p) ? "dense_group_x2_tma" : "dense_registers";

@@ -36,21 +36,24 @@ import torch
 
 
 def stan_epochs(warmup_duration=1000, init_duration=75, term_duration=50, base_duration=25):
-    """[(kind, duration)] with kind in {"fast", "slow"} — ``goose/warmup.py:12-88``."""
+    """
+    Stan-style warm-up schedule as ``[(kind, duration)]`` with kind "fast" (step size only) or "slow"
+    (step size + mass matrix), the schedule of ``goose/warmup.py:12-88``: an initial fast window, slow
+    windows that double in length for as long as the NEXT doubled window would still fit, one last slow
+    window that absorbs the remainder, and a closing fast window.
+    """
     if warmup_duration < 20:
         raise ValueError("warmup_duration too short (< 20)")
     if warmup_duration < init_duration + term_duration + base_duration:
         raise ValueError("warmup_duration too short (< init_duration + term_duration + base_duration)")
-    epochs = [("fast", init_duration)]
-    time_left = warmup_duration - init_duration - term_duration
-    this_time = base_duration
-    while 3 * this_time <= time_left:
-        epochs.append(("slow", this_time))
-        time_left -= this_time
-        this_time *= 2
-    epochs.append(("slow", time_left))
-    epochs.append(("fast", term_duration))
-    return epochs
+    slow_budget = warmup_duration - init_duration - term_duration
+    slow, window = [], base_duration
+    # a window of length w is followed by one of 2w: emit w only while w + 2w still fits
+    while slow_budget - sum(slow) >= 3 * window:
+        slow.append(window)
+        window *= 2
+    slow.append(slow_budget - sum(slow))
+    return [("fast", init_duration)] + [("slow", d) for d in slow] + [("fast", term_duration)]
 
 
 def _leaf_idx_to_ckpt_idxs(n: int):

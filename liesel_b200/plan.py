@@ -56,7 +56,7 @@ class Plan:
                     else:
                         x = torch.as_tensor(blk.x, device=dev).to(dt).contiguous()
                         knots = torch.as_tensor(np.asarray(blk.knots), device=dev).to(dt)
-                        start, w = _lib.spline_basis(x, knots)
+                        start, w = _lib.spline_basis(x, knots, blk.order)
                     rows[f"s{b}"], rows[f"w{b}"] = start, w
                 elif blk.kind == KIND_GROUP:
                     rows[f"g{b}"] = torch.as_tensor(blk.idx, device=dev).to(torch.int32).contiguous()

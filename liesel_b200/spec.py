@@ -210,8 +210,9 @@ class ModelSpec:
     ) -> "ModelSpec":
         """
         ``add_np_smooth`` whose design matrix is ``basis_matrix(x, knots, order)``
-        (reference ``contrib/splines.py:109-198``), kept in banded form: per row the first
-        non-zero column ``start`` and ``order + 1`` weights.
+        (reference ``contrib/splines.py:109-198``; orders 0..3), kept in banded form: per row the
+        first column ``start`` of a window of FOUR weights (orders below 3 leave the rest of the window
+        zero).
 
         ``center``: the design matrix is the column-centred basis ``B - 1 cbar^T`` (what a Liesel
         user passes to ``add_np_smooth`` so that the smooth is identified next to an intercept).
@@ -221,12 +222,12 @@ class ModelSpec:
         """
         pred = self._check_predictor(predictor)
         self._check_name(name)
-        if order != 3:
-            raise ValueError(f"only cubic B-splines (order=3) are implemented on the device, got order={order}")
+        if order not in (0, 1, 2, 3):
+            raise ValueError(f"B-spline orders 0..3 are implemented on the device, got order={order}")
         knots = np.sort(np.asarray(knots, dtype=self.dtype))  # splines.py:183
         k = knots.shape[0] - order - 1
-        if k < order + 1:
-            raise ValueError("too few knots for a cubic basis")
+        if k < 4:
+            raise ValueError("too few knots: the banded layout needs at least 4 basis functions")
         x = None if x is None else np.ascontiguousarray(np.asarray(x), dtype=self.dtype)
         if x is not None and x.shape != (self.n,):
             raise ValueError("x must be a 1d array with one entry per observation")
@@ -245,10 +246,10 @@ class ModelSpec:
                 raise ValueError("a precomputed band needs both start and weights")
             blk.start = np.ascontiguousarray(start, dtype=np.int32)
             blk.weights = np.ascontiguousarray(weights, dtype=self.dtype)
-            if blk.start.shape != (self.n,) or blk.weights.shape != (self.n, order + 1):
-                raise ValueError(f"band must be start [n] and weights [n, {order + 1}]")
-            if self.n and (blk.start.min() < 0 or blk.start.max() > k - (order + 1)):
-                raise ValueError(f"band start out of range: need 0 <= start <= {k - (order + 1)}")
+            if blk.start.shape != (self.n,) or blk.weights.shape != (self.n, 4):
+                raise ValueError("band must be start [n] and weights [n, 4] (orders < 3: zero-padded window)")
+            if self.n and (blk.start.min() < 0 or blk.start.max() > k - 4):
+                raise ValueError(f"band start out of range: need 0 <= start <= {k - 4}")
         self.blocks.append(blk)
         return self._relayout()
 

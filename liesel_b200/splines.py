@@ -48,9 +48,9 @@ def pspline_penalty(d: int, diff: int = 2) -> np.ndarray:
 def basis_matrix(x, knots, order: int = 3, outer_ok: bool = False, device=None):
     """
     Banded B-spline basis on the device: returns ``(start, weights)`` torch tensors with
-    ``start`` int32 [n] and ``weights`` [n, order+1] such that the reference's dense
+    ``start`` int32 [n] and ``weights`` [n, 4] such that the reference's dense
     ``basis_matrix(x, knots, order)[i, start[i] + t] == weights[i, t]`` and all other
-    entries of row i are zero.
+    entries of row i are zero (for ``order < 3`` some entries of the window are zero too).
 
     ``outer_ok=False`` raises if any x lies outside the interior knot range
     ``[knots[order], knots[-order-1]]`` (the documented behaviour of the reference's flag;
@@ -61,8 +61,8 @@ def basis_matrix(x, knots, order: int = 3, outer_ok: bool = False, device=None):
 
     from . import _lib
 
-    if order != 3:
-        raise ValueError("the device basis kernel implements cubic splines (order=3)")
+    if order not in (0, 1, 2, 3):
+        raise ValueError("the device basis kernel implements B-spline orders 0..3")
     knots = np.sort(np.asarray(knots))
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(np.ascontiguousarray(np.atleast_1d(x), dtype=knots.dtype))
@@ -76,4 +76,4 @@ def basis_matrix(x, knots, order: int = 3, outer_ok: bool = False, device=None):
                 "Values of x are not inside the range of interior knots, "
                 f"[{knots[order]}, {knots[knots.shape[0] - order - 1]}]"
             )
-    return _lib.spline_basis(x, torch.as_tensor(knots, device=dev))
+    return _lib.spline_basis(x, torch.as_tensor(knots, device=dev), order)

@@ -1017,3 +1017,56 @@ def test_nuts_gibbs_on_device_converges(lb):
     B = OSp.basis_matrix(xs, np.asarray(blk.knots, dtype=np.float64), 3)
     fit = q[0] + B @ q[blk.param_offset: blk.param_offset + blk.ncoef]
     np.testing.assert_allclose(fit, 1.0 + np.sin(2 * np.pi * xs), atol=0.05)
+
+
+# --- B-spline orders below 3 (contrib/splines.py:109-198 is order-generic) -----------------------------
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_basis_other_orders_bit_exact(lb, order, dtype):
+    """The device band is four wide for every order; scattered into the dense [n, k] matrix it must be
+    bit-identical to the oracle's dense recursion (index AND weights), adversarial points included."""
+    from liesel_b200 import splines
+
+    rng = np.random.default_rng(4 + order)
+    x = rng.uniform(size=50_000).astype(dtype)
+    knots = splines.equidistant_knots(x, 12, order)
+    edge = np.concatenate([knots, np.nextafter(knots, dtype(np.inf)), np.nextafter(knots, dtype(-np.inf))])
+    x = np.concatenate([x, edge.astype(dtype), [knots[0] - 1, knots[-1] + 1]]).astype(dtype)
+    start, w = splines.basis_matrix(x, knots, order, outer_ok=True, device="cuda")
+    start, w = start.cpu().numpy(), w.cpu().numpy()
+    k = knots.shape[0] - order - 1
+    assert w.shape == (x.shape[0], 4) and start.min() >= 0 and start.max() <= k - 4
+    dense = OS.band_to_dense(start, w, k)
+    assert np.array_equal(dense, OS.basis_matrix(x, knots, order))
+    assert (np.count_nonzero(w, axis=1) <= order + 1).all()
+
+
+@pytest.mark.parametrize("order,C", [(1, 40), (2, 40), (2, 320)])
+def test_logp_grad_lower_order_splines(lb, order, C):
+    """Location-scale model with linear / quadratic P-splines through the scalar run-length kernel
+    (C = 40) and the packed kernel (C = 320), against the oracle (which builds its own order + 1 wide
+    band from the same x and knots)."""
+    from liesel_b200.spec import ModelSpec
+    from liesel_b200.splines import equidistant_knots, pspline_penalty
+
+    rng = np.random.default_rng(11)
+    n, k = 30_000, 14
+    x = rng.uniform(size=n)
+    y = rng.normal(1.0 + np.sin(2 * np.pi * x), np.exp(-0.5 + 0.5 * np.cos(2 * np.pi * x)))
+    spec = ModelSpec(dtype=np.dtype(np.float32))
+    spec.add_response(y, "normal").add_predictor("loc").add_predictor("scale")
+    xd = x.astype(np.float32)
+    knots = equidistant_knots(xd, k, order)
+    K = pspline_penalty(k, 2)
+    spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, "loc", "loc_p0")
+    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "loc", "loc_np0", order=order, tau2_init=1.0)
+    spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, "scale", "scale_p0")
+    spec.add_spline_smooth(xd, knots, K, 1.0, 0.005, "scale", "scale_np0", order=order, tau2_init=1.0)
+    plan = lb.Plan(spec)
+    assert plan.variant == "banded_tma_runlength"
+    rng2 = np.random.default_rng(12)
+    th = (0.2 * rng2.normal(size=(C, spec.num_params))).astype(np.float32)
+    th[:, 0] += 1.0
+    aux = np.exp(rng2.uniform(-2, 2, size=(C, 2))).astype(np.float32)
+    check_logp_grad(spec, plan, th, aux, chains=[0, 1, C // 2, C - 1])
+    check_iwls(spec, plan, "loc_np0", th, aux, chains=[0, C - 1])
