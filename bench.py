@@ -216,7 +216,7 @@ def measure_pipe_peaks(torch, _lib, sm_count):
         for rep in range(4):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            _lib.check(_lib.lib.lslb_debug_pipe_peak(kind, sm_count * 8, iters, _lib.ptr(sink),
+            _lib.check(_lib.bench_lib().lslb_debug_pipe_peak(kind, sm_count * 8, iters, _lib.ptr(sink),
                                                      C.byref(work), _lib.stream_ptr()), "pipe_peak")
             e.record()
             torch.cuda.synchronize()

@@ -326,23 +326,15 @@ int lslb_nuts_leaf_post_f32(void* const* ptrs, const int* ints, double div_thr, 
 int lslb_nuts_leaf_post_f64(void* const* ptrs, const int* ints, double div_thr, lslb_stream_t stream);
 
 /*
- * Measurement hooks (used by bench.py; no effect on results).
+ * Measurement hook (used by bench.py; no effect on results).
  * lslb_debug_set_events: the given cudaEvent_t pair is recorded on the call's stream immediately
  *   before and after the dominant row-streaming kernel of every following lslb_logp_grad_* /
  *   lslb_iwls_* call made from this host thread (NULL, NULL switches it off).
- * lslb_debug_pipe_peak: micro-benchmarks giving measured pipe peaks; kind 0 = FP32 FMA,
- *   1 = packed fma.rn.f32x2, 2 = MUFU ex2, 3 = shared-memory 4-byte loads. *work (host) receives
- *   the operations one launch performs.
+ * (The pipe-peak micro-benchmarks and the tcgen05 probe are NOT part of this library: see
+ *  include/liesel_b200_bench.h / libliesel_b200_bench.so.)
  */
 int lslb_debug_set_events(void* start_event, void* stop_event);
 int lslb_debug_event_count(void);
-int lslb_debug_pipe_peak(int kind, int blocks, int iters, float* sink, double* work,
-                         lslb_stream_t stream);
-/* tcgen05 building block under test: D [128 x N] = A [128 x K] . B [N x K]^T via TMA + tcgen05.mma
- * kind::tf32 (split bit 0: three-pass hi/lo split, fp32-level accuracy; bit 1: K chunks of 16 floats
- * with the 64-byte swizzle instead of 32 floats with the 128-byte swizzle). N in {64,128,256}, K % 32 == 0. */
-int lslb_debug_tc_probe(const float* A, const float* B, int N, int K, int split, float* D,
-                        lslb_stream_t stream);
 
 #ifdef __cplusplus
 }

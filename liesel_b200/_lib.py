@@ -140,19 +140,31 @@ for _sfx in ("f32", "f64"):
 lib.lslb_debug_set_events.restype = _i
 lib.lslb_debug_set_events.argtypes = [_vp, _vp]
 lib.lslb_debug_event_count.restype = _i
-lib.lslb_debug_pipe_peak.restype = _i
-lib.lslb_debug_pipe_peak.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_double), _vp]
 
-lib.lslb_debug_tc_probe.restype = _i
-lib.lslb_debug_tc_probe.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
+BENCH_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libliesel_b200_bench.so")
+BENCH_EXPORTS = ["lslb_debug_pipe_peak", "lslb_debug_tc_probe"]
+_bench_lib = None
+
+
+def bench_lib():
+    """The TOOLS library (pipe-peak micro-benchmarks, tcgen05 probe; ``include/liesel_b200_bench.h``),
+    loaded on first use by bench.py and tools/ — the product path never touches it."""
+    global _bench_lib
+    if _bench_lib is None:
+        b = C.CDLL(BENCH_LIB_PATH)
+        b.lslb_debug_pipe_peak.restype = _i
+        b.lslb_debug_pipe_peak.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_double), _vp]
+        b.lslb_debug_tc_probe.restype = _i
+        b.lslb_debug_tc_probe.argtypes = [_vp, _vp, _i, _i, _i, _vp, _vp]
+        _bench_lib = b
+    return _bench_lib
 
 EXPORTS = [
     "lslb_peer_create", "lslb_peer_connect", "lslb_peer_destroy", "lslb_peer_timed_out", "lslb_peer_abort", "lslb_peer_reset",
     "lslb_logp_grad_peer_f32", "lslb_logp_grad_peer_f64", "lslb_iwls_peer_f32", "lslb_iwls_peer_f64",
     "lslb_nccl_unique_id", "lslb_nccl_comm_create", "lslb_nccl_comm_destroy",
     "lslb_logp_grad_nccl_f32", "lslb_logp_grad_nccl_f64", "lslb_iwls_nccl_f32", "lslb_iwls_nccl_f64",
-    "lslb_debug_tc_probe",
-    "lslb_debug_set_events", "lslb_debug_event_count", "lslb_debug_pipe_peak",
+    "lslb_debug_set_events", "lslb_debug_event_count",
     "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
     "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_dtype", "lslb_plan_block_ncoef", "lslb_plan_variant", "lslb_plan_kernel_name",

@@ -31,7 +31,7 @@ namespace lslb {
 
 typedef unsigned long long u64t;
 int make_tmap_f32_k32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
-                      int box_rows);  // tc_probe.cu
+                      int box_rows);  // tmap.cu
 int make_tmap_f32(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
                   int kc);
 

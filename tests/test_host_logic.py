@@ -84,6 +84,13 @@ def test_c_abi_exports_every_declared_symbol():
     from liesel_b200 import _lib
 
     assert sorted(_lib.EXPORTS) == declared
+    # the tools library (micro-benchmarks, tcgen05 probe) is separate: its symbols are NOT in the product
+    bheader = open(os.path.join(ROOT, "include", "liesel_b200_bench.h")).read()
+    bdeclared = sorted(set(re.findall(r"\b(lslb_[a-z0-9_]+)\s*\(", bheader)))
+    assert bdeclared == sorted(_lib.BENCH_EXPORTS)
+    blib = ctypes.CDLL(_lib.BENCH_LIB_PATH)
+    for name in bdeclared:
+        assert hasattr(blib, name) and not hasattr(lib, name), name
 
 
 def test_no_cpu_fallback():

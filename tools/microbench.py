@@ -23,7 +23,7 @@ for kind, name, iters, scale in [(0, "ffma_tflops", 4000, 2e-12), (1, "ffma2_tfl
     for rep in range(5):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        _lib.check(_lib.lib.lslb_debug_pipe_peak(kind, sm * 8, iters, _lib.ptr(sink), C.byref(work),
+        _lib.check(_lib.bench_lib().lslb_debug_pipe_peak(kind, sm * 8, iters, _lib.ptr(sink), C.byref(work),
                                                  _lib.stream_ptr()), "pipe_peak")
         e.record()
         torch.cuda.synchronize()

@@ -14,7 +14,7 @@ for N, K in [(128, 32), (128, 64), (64, 256), (256, 256)]:
     ref = (A.double() @ B.double().T)
     for split in (0, 1, 2, 3, 4):  # bit 0: 3-pass hi/lo split; bit 1: 16-float chunks (64-byte swizzle)
         D = torch.zeros(128, N, device="cuda")
-        st = _lib.lib.lslb_debug_tc_probe(_lib.ptr(A), _lib.ptr(B), N, K, split, _lib.ptr(D), _lib.stream_ptr())
+        st = _lib.bench_lib().lslb_debug_tc_probe(_lib.ptr(A), _lib.ptr(B), N, K, split, _lib.ptr(D), _lib.stream_ptr())
         torch.cuda.synchronize()
         err = (D.double() - ref).abs().max().item()
         scale = ref.abs().max().item()
