@@ -334,7 +334,15 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.ntiles_total = (int)((plan->desc.n + BR - 1) / BR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
   int ctas_per_sm = x2 ? 16 / (k.tc_eff / 64) : 6;  // x2: at most 16 resident warps per SM (registers)
-  if (ctas_per_sm > (x2 ? 6 : 5)) ctas_per_sm = x2 ? 6 : 5;  // shared memory: 34 KB of row stages per CTA
+  if (x2) {
+    // shared memory: 5.7 KB per ring stage. 16 one-warp CTAs take 2 stages each, 8 two-warp CTAs 3, the
+    // rest 6 (until round 2 every CTA had 6 stages = 34 KB, which capped an SM at 6 CTAs: 6 warps at
+    // 64 chains, 12 at 128)
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    k.stages = ctas_per_sm >= 16 ? 2 : (ctas_per_sm >= 8 ? 3 : 6);
+  } else if (ctas_per_sm > 5) {
+    ctas_per_sm = 5;  // shared memory of the scalar kernel's row stages
+  }
   static const int knob_ctas = [] {  // tuning knob, read once
     const char* e = getenv("LSLB_BANDED_CTAS_PER_SM");
     return e ? atoi(e) : 0;

@@ -46,7 +46,10 @@ __device__ __forceinline__ unsigned x2_smid() {
 // UNITY: every row's four weights sum to one (all x inside the knot range; checked at plan creation).
 // Then, over a run of equal spans, eta = b1 + sum_{u != 1} w_u (b_u - b1) and the gradient of b1 is
 // (sum of residuals) - g0 - g2 - g3: three FMAs per smooth and direction instead of four.
-template <int FAM, int NS, int PM, bool GRAD, bool UNITY>
+// X2S: depth of the TMA ring (tiles the fastest warp may run ahead of the slowest). 6 for the 4..16-warp
+// CTAs; the 2- and 1-warp CTAs of small chain counts take 3 and 2 stages so that 8 / 16 of them fit an
+// SM's shared memory (with 6 stages = 34 KB each only 6 did: 6 resident warps at 64 chains).
+template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S>
 #ifndef LSLB_X2_NRB
 #define LSLB_X2_NRB 4   // rows per register block (4 or 2)
 #endif
@@ -55,7 +58,6 @@ template <int FAM, int NS, int PM, bool GRAD, bool UNITY>
 #endif
 __global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA (or 2 x 8, 4 x 4 for few chains)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
-  constexpr int X2S = LSLB_X2_STAGES;
   __shared__ __align__(128) XRaw<NS> raw[X2S];
   __shared__ __align__(8) u64 full[X2S];
   __shared__ int done[X2S];  // warps that have finished with the tile in stage s
@@ -520,13 +522,20 @@ static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cu
   // a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps): the kernel's index arithmetic
   // and cooperative loads are written in terms of blockDim.x
   dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff / 2);
-  if (unity) {
-    if (g) banded_x2_kernel<FAM, NS, PM, true, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
-    else banded_x2_kernel<FAM, NS, PM, false, true><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
-  } else {
-    if (g) banded_x2_kernel<FAM, NS, PM, true, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
-    else banded_x2_kernel<FAM, NS, PM, false, false><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);
-  }
+#define LSLB_X2_GO(ST)                                                                                           \
+  do {                                                                                                           \
+    if (unity) {                                                                                                 \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);   \
+      else banded_x2_kernel<FAM, NS, PM, false, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);    \
+    } else {                                                                                                     \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);  \
+      else banded_x2_kernel<FAM, NS, PM, false, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);   \
+    }                                                                                                            \
+  } while (0)
+  if (k.stages >= LSLB_X2_STAGES) LSLB_X2_GO(LSLB_X2_STAGES);
+  else if (k.stages == 3) LSLB_X2_GO(3);
+  else LSLB_X2_GO(2);
+#undef LSLB_X2_GO
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }
