@@ -49,6 +49,7 @@ struct SplP {
   int pred;
   int pad;
   const float* tw;   // banded_x2 only: per 128-row tile the column sums of w, [ntiles][4] (plan-owned)
+  const float* wp;   // banded_iwls_x2 only: per row the ten products w_a w_b (a <= b), [n][12] (plan-owned) or NULL
 };
 template <typename T>
 struct DnsP {
@@ -227,6 +228,7 @@ struct lslb_plan {
   float* d_XT;       // tensor-core path (or NULL): plan-owned hi part of the transposed dense block [p x n_pad]
   float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
   float* d_tw[LSLB_MAX_SPL];   // float32 banded plans: per 128-row tile the column sums of each smooth's weights
+  float* d_wp[LSLB_MAX_SPL];   // float32 banded Normal plans: per row the products w_a w_b of each smooth ([n][12])
   long long n_pad;
   bool tc_two_pass;  // tensor-core path: two TF32 passes per product are enough for this data (plan-time check)
   int variant;

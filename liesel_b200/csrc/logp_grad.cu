@@ -292,7 +292,18 @@ __device__ __forceinline__ void finalize_grad_body(const FinalizeParams& fp, con
   double acc = 0.0;
   const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
   const T* src = partial + (size_t)j * fp.Cpad + c;
-  for (int ch = g; ch < fp.nchunks; ch += FIN_G) acc += (double)src[ch * stride];
+  // eight loads in flight per thread, summed in the order of the plain loop (bitwise the same result):
+  // with one load per iteration the kernel ran at the latency of nchunks / FIN_G dependent round trips
+  // (24-33 us for 22-27 MB of partials, 0.9 TB/s)
+  int ch = g;
+  for (; ch + 7 * FIN_G < fp.nchunks; ch += 8 * FIN_G) {
+    T v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(ch + u * FIN_G) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+  }
+  for (; ch < fp.nchunks; ch += FIN_G) acc += (double)src[(size_t)ch * stride];
   red[g][threadIdx.x] = acc;
   __syncthreads();
   if (g != 0 || c >= fp.C) return;
@@ -353,7 +364,20 @@ __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, con
   const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
   const T* lo = hi + fp.Cpad;
   double acc = 0.0;
-  for (int ch = g; ch < fp.nchunks_logp; ch += FIN_G) acc += (double)hi[ch * stride] - (double)lo[ch * stride];
+  {
+    int ch = g;
+    for (; ch + 3 * FIN_G < fp.nchunks_logp; ch += 4 * FIN_G) {
+      T vh[4], vl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vh[u] = hi[(size_t)(ch + u * FIN_G) * stride];
+        vl[u] = lo[(size_t)(ch + u * FIN_G) * stride];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += (double)vh[u] - (double)vl[u];
+    }
+    for (; ch < fp.nchunks_logp; ch += FIN_G) acc += (double)hi[(size_t)ch * stride] - (double)lo[(size_t)ch * stride];
+  }
   // quadratic forms of the priors, coefficient rows j = g, g + FIN_G, ... (already scaled)
   if (with_prior) {
     const int cc = c < fp.C ? c : 0;
@@ -593,7 +617,7 @@ void fill_eval_params(const lslb_plan* plan, EvalParams<T>& ep, int C, int Cpad)
   for (int m = 0; m < plan->ns; ++m) {
     const lslb_block_desc& d = plan->blk[plan->sp[m]];
     ep.sp[m] = {reinterpret_cast<const T*>(d.data), d.index, plan->soff[plan->sp[m]], d.ncoef,
-                d.predictor, 0, plan->d_tw[m]};
+                d.predictor, 0, plan->d_tw[m], plan->d_wp[m]};
   }
   for (int m = 0; m < plan->nd; ++m) {
     const lslb_block_desc& d = plan->blk[plan->dn[m]];

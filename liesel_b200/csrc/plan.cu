@@ -103,6 +103,18 @@ __global__ void tile_weight_sums_kernel(const float* __restrict__ w, long long n
   }
 }
 
+// per row the ten products w_a w_b (a <= b) of one spline block's weights, padded to 12 floats: the
+// IWLS kernel's Gram update reads them as broadcast scalars (they are the same for every chain)
+__global__ void weight_products_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float4 v = *reinterpret_cast<const float4*>(w + 4 * r);
+  float4* o = reinterpret_cast<float4*>(out + 12 * r);
+  o[0] = make_float4(v.x * v.x, v.x * v.y, v.x * v.z, v.x * v.w);
+  o[1] = make_float4(v.y * v.y, v.y * v.z, v.y * v.w, v.z * v.z);
+  o[2] = make_float4(v.z * v.w, v.w * v.w, 0.f, 0.f);
+}
+
 // sum_i lgamma(y_i + 1) in double, one block, fixed order (deterministic)
 template <typename T>
 __global__ void lgamma_sum_kernel(const T* __restrict__ y, long long n, double* out) {
@@ -352,6 +364,19 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
       if (e == cudaSuccess)
         tile_weight_sums_kernel<<<(unsigned)ntiles, 128>>>((const float*)p->blk[p->sp[m]].data, n, p->d_tw[m]);
     }
+    // IWLS of the Normal families runs the packed kernel (banded_iwls_x2.cu): weight products of every
+    // smooth, 48 bytes per row (LSLB_NO_IWLS_PAIRS=1 skips them; the kernel then multiplies per chain)
+    const char* nop = getenv("LSLB_NO_IWLS_PAIRS");
+    if (!(nop && atoi(nop) != 0) && banded_fast_eligible(p) &&
+        (p->fam == FAM_NORMAL_LS || p->fam == FAM_NORMAL_FIXED)) {
+      for (int m = 0; m < p->ns && e == cudaSuccess; ++m) {
+        if ((reinterpret_cast<uintptr_t>(p->blk[p->sp[m]].data) & 15) != 0) continue;
+        e = cudaMalloc(&p->d_wp[m], sizeof(float) * 12 * (size_t)n);
+        if (e == cudaSuccess)
+          weight_products_kernel<<<(unsigned)((n + 255) / 256), 256>>>((const float*)p->blk[p->sp[m]].data, n,
+                                                                        p->d_wp[m]);
+      }
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       set_cuda_error(e, "tile weight sums");
@@ -368,6 +393,8 @@ extern "C" void lslb_plan_destroy(lslb_plan* p) {
   if (p->d_chunk_start) cudaFree(p->d_chunk_start);
   for (int m = 0; m < LSLB_MAX_SPL; ++m)
     if (p->d_tw[m]) cudaFree(p->d_tw[m]);
+  for (int m = 0; m < LSLB_MAX_SPL; ++m)
+    if (p->d_wp[m]) cudaFree(p->d_wp[m]);
   lslb::dense_tc_release(p);
   delete p;
 }
