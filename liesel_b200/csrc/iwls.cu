@@ -178,6 +178,23 @@ iwls_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ Iwl
   for (int j = 0; j < q.nq; ++j) out[(size_t)j * p.Cpad] = as[j * TC + tid];
 }
 
+// sum over the chunk partials of one (row, chain) entry in double, chunk order; eight loads in flight
+// (the plain loop is a chain of nchunks dependent L2 round trips: 592 at the S3 size)
+template <typename T>
+__device__ __forceinline__ double chunk_sum(const T* __restrict__ src, size_t stride, int nchunks) {
+  double acc = 0.0;
+  int ch = 0;
+  for (; ch + 8 <= nchunks; ch += 8) {
+    T v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(ch + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+  }
+  for (; ch < nchunks; ++ch) acc += (double)src[(size_t)ch * stride];
+  return acc;
+}
+
 // Sums the chunk partials into chunk 0 (each thread owns one (row, chain) column, fixed order).
 // Used before the finalize step of a centred spline block, whose correction needs whole sums.
 template <typename T>
@@ -185,9 +202,7 @@ __global__ void iwls_reduce_kernel(T* partial, int nq, int Cpad, int nchunks) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)nq * Cpad;
   if (idx >= stride) return;
-  double acc = 0.0;
-  for (int ch = 0; ch < nchunks; ++ch) acc += (double)partial[ch * stride + idx];
-  partial[idx] = (T)acc;
+  partial[idx] = (T)chunk_sum(partial + idx, (size_t)stride, nchunks);
 }
 
 // score [C x p], info [C x p x p] from the chunk partials + prior terms.
@@ -226,7 +241,7 @@ __global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, 
   if (e < p) {
     double acc = 0.0;
     const T* src = partial + (size_t)e * fp.Cpad + c;
-    for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+    acc = chunk_sum(src, stride, fp.nchunks);
     if (center) {
       double R = 0.0;
       for (int j = 0; j < p; ++j) R += red(j);
@@ -258,7 +273,7 @@ __global__ void iwls_finalize_kernel(const __grid_constant__ FinalizeParams fp, 
   }
   if (row >= 0) {
     const T* src = partial + (size_t)row * fp.Cpad + c;
-    for (int ch = 0; ch < fp.nchunks; ++ch) acc += (double)src[ch * stride];
+    acc = chunk_sum(src, stride, fp.nchunks);
   }
   if (center) {
     double omega = 0.0;
@@ -612,9 +627,7 @@ int launch_iwls(const lslb_plan* plan, int C, int block, const T* params, const 
   q.nq = nq;
   q.partial = L.partial;
 
-  long long total = (long long)plan->Psmall * k.Cpad;
-  gather_small_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fp, params, L.pT);
-  LSLB_LAUNCH_CHECK();
+  if (int gst = launch_gather_small<T>(fp, params, L.pT, stream)) return gst;
   if (plan->grp >= 0) {
     const lslb_block_desc& d = plan->blk[plan->grp];
     dim3 grid((d.ncoef + 31) / 32, (k.Cpad + 31) / 32), blockd(32, 8);

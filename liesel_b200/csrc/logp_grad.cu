@@ -284,55 +284,71 @@ eval_kernel(const __grid_constant__ EvalParams<T> p, int fstride) {
 template <typename T, int FIN_G>
 __device__ __forceinline__ void finalize_grad_body(const FinalizeParams& fp, const T* __restrict__ partial,
                                                    const T* __restrict__ pT, const T* __restrict__ aux,
-                                                   T* __restrict__ grad, T* __restrict__ vsum) {
+                                                   T* __restrict__ grad, T* __restrict__ vsum,
+                                                   double* __restrict__ qf) {
+  // One CTA per (32 chains, coefficient row j). It reduces the row's chunk partials (gradient of the
+  // likelihood), adds the prior's gradient and ALSO emits the row's share of the prior's quadratic
+  // form, qf[j][c] = -1/2 x_j (K x)_j / tau2 (or -1/2 (x_j - m)^2 / s^2): the log-posterior kernel
+  // then only sums Psmall numbers per chain. (Until round 2 the log-posterior slice recomputed K x
+  // for every block inside ONE CTA per 32 chains: 25-30 us on the critical path of every call.)
+  // grad == NULL (value-only call): the prior part alone.
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y;
   const int g = threadIdx.y;
   double acc = 0.0;
-  const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
-  const T* src = partial + (size_t)j * fp.Cpad + c;
-  // eight loads in flight per thread, summed in the order of the plain loop (bitwise the same result):
-  // with one load per iteration the kernel ran at the latency of nchunks / FIN_G dependent round trips
-  // (24-33 us for 22-27 MB of partials, 0.9 TB/s)
-  int ch = g;
-  for (; ch + 7 * FIN_G < fp.nchunks; ch += 8 * FIN_G) {
-    T v[8];
+  if (grad != nullptr) {
+    const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
+    const T* src = partial + (size_t)j * fp.Cpad + c;
+    // eight loads in flight per thread, summed in the order of the plain loop
+    int ch = g;
+    for (; ch + 7 * FIN_G < fp.nchunks; ch += 8 * FIN_G) {
+      T v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(ch + u * FIN_G) * stride];
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(ch + u * FIN_G) * stride];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc += (double)v[u];
+      for (int u = 0; u < 8; ++u) acc += (double)v[u];
+    }
+    for (; ch < fp.nchunks; ch += FIN_G) acc += (double)src[(size_t)ch * stride];
+    red[g][threadIdx.x] = acc;
+    __syncthreads();
   }
-  for (; ch < fp.nchunks; ch += FIN_G) acc += (double)src[(size_t)ch * stride];
-  red[g][threadIdx.x] = acc;
-  __syncthreads();
-  if (g != 0 || c >= fp.C) return;
+  if (g != 0) return;
   acc = 0.0;
+  if (grad != nullptr) {
 #pragma unroll
-  for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
-  if (j >= fp.Preal) {  // residual sum of a predictor with centred splines: used by center_fix_kernel
-    vsum[(size_t)(j - fp.Preal) * fp.Cpad + c] = (T)acc;
-    return;
+    for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
   }
-  for (int b = 0; b < fp.nblocks; ++b) {
-    const PriorP& pr = fp.pr[b];
-    if (pr.soff < 0 || j < pr.soff || j >= pr.soff + pr.ncoef) continue;
-    int jj = j - pr.soff;
-    if (!(fp.flags & LSLB_SKIP_PRIOR)) {
-      if (pr.prior == LSLB_PRIOR_NORMAL) {
-        acc -= ((double)pT[(size_t)j * fp.Cpad + c] - pr.m) * pr.inv_s2;
-      } else if (pr.prior == LSLB_PRIOR_MVND) {
-        const T* K = reinterpret_cast<const T*>(pr.K) + (size_t)jj * pr.ncoef;
-        double kb = 0.0;
-        for (int i = 0; i < pr.ncoef; ++i)
-          kb += (double)K[i] * (double)pT[(size_t)(pr.soff + i) * fp.Cpad + c];
-        double tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)c * fp.A + pr.tau2_slot] : pr.tau2_fixed;
-        acc -= kb / tau2;
+  double q = 0.0;
+  if (c < fp.C) {
+    if (j >= fp.Preal) {  // residual sum of a predictor with centred splines: used by center_fix_kernel
+      if (grad != nullptr) vsum[(size_t)(j - fp.Preal) * fp.Cpad + c] = (T)acc;
+    } else {
+      for (int b = 0; b < fp.nblocks; ++b) {
+        const PriorP& pr = fp.pr[b];
+        if (pr.soff < 0 || j < pr.soff || j >= pr.soff + pr.ncoef) continue;
+        int jj = j - pr.soff;
+        if (!(fp.flags & LSLB_SKIP_PRIOR)) {
+          const double xj = (double)pT[(size_t)j * fp.Cpad + c];
+          if (pr.prior == LSLB_PRIOR_NORMAL) {
+            acc -= (xj - pr.m) * pr.inv_s2;
+            q = -0.5 * pr.inv_s2 * (xj - pr.m) * (xj - pr.m);
+          } else if (pr.prior == LSLB_PRIOR_MVND) {
+            const T* K = reinterpret_cast<const T*>(pr.K) + (size_t)jj * pr.ncoef;
+            double kb = 0.0;
+            for (int i = 0; i < pr.ncoef; ++i)
+              kb += (double)K[i] * (double)pT[(size_t)(pr.soff + i) * fp.Cpad + c];
+            double tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)c * fp.A + pr.tau2_slot] : pr.tau2_fixed;
+            acc -= kb / tau2;
+            q = -0.5 * (kb * xj) / tau2;  // row j of x' K x (mvn_degen.py:442)
+          }
+        }
+        if (grad != nullptr) grad[(size_t)c * fp.P + pr.off + jj] = (T)acc;
+        break;
       }
     }
-    grad[(size_t)c * fp.P + pr.off + jj] = (T)acc;
-    break;
   }
+  qf[(size_t)j * fp.Cpad + c] = q;
 }
 
 // grad[c, block] -= cbar * (residual sum of the block's predictor): the rank-one part of
@@ -354,58 +370,24 @@ template <typename T, int FIN_G>
 __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, const T* __restrict__ partial,
                                                    const T* __restrict__ pT, const T* __restrict__ aux,
                                                    const T* __restrict__ gpl, int gtiles, int G,
-                                                   T* __restrict__ logp) {
+                                                   const double* __restrict__ qf, T* __restrict__ logp) {
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;  // < Cpad (Cpad is a multiple of 32)
   const int g = threadIdx.y;
   const bool with_prior = !(fp.flags & LSLB_SKIP_PRIOR);
   (void)G;
-  const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
-  const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
-  const T* lo = hi + fp.Cpad;
-  double acc = 0.0;
-  {
-    int ch = g;
-    for (; ch + 3 * FIN_G < fp.nchunks_logp; ch += 4 * FIN_G) {
-      T vh[4], vl[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vh[u] = hi[(size_t)(ch + u * FIN_G) * stride];
-        vl[u] = lo[(size_t)(ch + u * FIN_G) * stride];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc += (double)vh[u] - (double)vl[u];
-    }
-    for (; ch < fp.nchunks_logp; ch += FIN_G) acc += (double)hi[(size_t)ch * stride] - (double)lo[(size_t)ch * stride];
-  }
-  // quadratic forms of the priors, coefficient rows j = g, g + FIN_G, ... (already scaled)
+  // log-likelihood: summed over the row chunks by the extra slice of finalize_rows_kernel (row Psmall of qf)
+  double acc = g == 0 ? qf[(size_t)fp.Psmall * fp.Cpad + c] : 0.0;
+  // quadratic forms of the priors: one number per coefficient row from finalize_grad_body, plus the
+  // group block's per-tile partials
   if (with_prior) {
-    const int cc = c < fp.C ? c : 0;
+    for (int j = g; j < fp.Preal; j += FIN_G) acc += qf[(size_t)j * fp.Cpad + c];
     for (int b = 0; b < fp.nblocks; ++b) {
       const PriorP& pr = fp.pr[b];
-      if (pr.prior == LSLB_PRIOR_NORMAL) {
+      if (pr.prior == LSLB_PRIOR_NORMAL && pr.soff < 0) {  // group block: reduced per 32-group tile
         double q = 0.0;
-        if (pr.soff >= 0) {
-          for (int j = g; j < pr.ncoef; j += FIN_G) {
-            double d = (double)pT[(size_t)(pr.soff + j) * fp.Cpad + c] - pr.m;
-            q += d * d;
-          }
-          q *= -0.5 * pr.inv_s2;
-        } else {  // group block: quadratic part was reduced per 32-group tile
-          for (int t = g; t < gtiles; t += FIN_G) q += (double)gpl[(size_t)t * fp.Cpad + c];
-        }
+        for (int t = g; t < gtiles; t += FIN_G) q += (double)gpl[(size_t)t * fp.Cpad + c];
         acc += q;
-      } else if (pr.prior == LSLB_PRIOR_MVND) {
-        const T* K = reinterpret_cast<const T*>(pr.K);
-        double q = 0.0;  // (x @ prec) @ x^T, mvn_degen.py:442
-        for (int j = g; j < pr.ncoef; j += FIN_G) {
-          double xk = 0.0;
-          for (int i = 0; i < pr.ncoef; ++i)
-            xk += (double)pT[(size_t)(pr.soff + i) * fp.Cpad + c] * (double)K[(size_t)i * pr.ncoef + j];
-          q += xk * (double)pT[(size_t)(pr.soff + j) * fp.Cpad + c];
-        }
-        double tau2 = pr.tau2_slot >= 0 ? (double)aux[(size_t)cc * fp.A + pr.tau2_slot] : pr.tau2_fixed;
-        acc += -0.5 * q / tau2;
       }
     }
   }
@@ -436,23 +418,56 @@ __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, con
   logp[c] = (T)acc;
 }
 
-// value only: one slice of blocks; value + gradient: grid.y = Psmall + 1, the last slice computes the
-// log-posterior while the others reduce the gradient rows (one launch, both run concurrently)
+// Extra slice of finalize_rows_kernel (blockIdx.y == Psmall): the chains' log-likelihood, summed over
+// the row chunks (Kahan pairs hi - lo) in double, into row Psmall of qf.
+template <typename T, int FIN_G>
+__device__ __forceinline__ void finalize_loglik_body(const FinalizeParams& fp, const T* __restrict__ partial,
+                                                     double* __restrict__ qf) {
+  __shared__ double red[FIN_G][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = threadIdx.y;
+  const size_t stride = (size_t)(fp.Psmall + LSLB_NACC) * fp.Cpad;
+  const T* hi = partial + (size_t)fp.Psmall * fp.Cpad + c;
+  const T* lo = hi + fp.Cpad;
+  double acc = 0.0;
+  int ch = g;
+  for (; ch + 3 * FIN_G < fp.nchunks_logp; ch += 4 * FIN_G) {
+    T vh[4], vl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vh[u] = hi[(size_t)(ch + u * FIN_G) * stride];
+      vl[u] = lo[(size_t)(ch + u * FIN_G) * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += (double)vh[u] - (double)vl[u];
+  }
+  for (; ch < fp.nchunks_logp; ch += FIN_G) acc += (double)hi[(size_t)ch * stride] - (double)lo[(size_t)ch * stride];
+  red[g][threadIdx.x] = acc;
+  __syncthreads();
+  if (g != 0) return;
+  acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < FIN_G; ++k) acc += red[k][threadIdx.x];
+  qf[(size_t)fp.Psmall * fp.Cpad + c] = acc;
+}
+
+// Two launches per call: finalize_rows_kernel (grid.y = Psmall: gradient rows + the rows' shares of the
+// priors' quadratic forms; value-only calls run it with grad == NULL) and finalize_logp_kernel (one CTA
+// per 32 chains: log-likelihood chunks + Psmall numbers + constants).
 template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
 finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
                      const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
-                     int gtiles, int G, T* __restrict__ logp) {
-  finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, logp);
+                     int gtiles, int G, const double* __restrict__ qf, T* __restrict__ logp) {
+  finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, qf, logp);
 }
 template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
-finalize_all_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
-                    const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
-                    T* __restrict__ vsum, const T* __restrict__ gpl, int gtiles, int G,
-                    T* __restrict__ logp) {
-  if ((int)blockIdx.y < fp.Psmall) finalize_grad_body<T, FIN_G>(fp, partial, pT, aux, grad, vsum);
-  else finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, logp);
+finalize_rows_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
+                     const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
+                     T* __restrict__ vsum, double* __restrict__ qf) {
+  if ((int)blockIdx.y < fp.Psmall) finalize_grad_body<T, FIN_G>(fp, partial, pT, aux, grad, vsum, qf);
+  else finalize_loglik_body<T, FIN_G>(fp, partial, qf);
 }
 
 // =======================================================================================
@@ -525,6 +540,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
 template <typename T>
 struct WsLayout {
   T *pT, *partial, *bT, *gbT, *gpl, *rt, *vsum;
+  double* qf;  // [(Psmall + 1) x Cpad] per-row shares of the priors' quadratic forms; last row: log-likelihood
   int gtiles;
   size_t bytes;
 };
@@ -541,6 +557,8 @@ static WsLayout<T> layout_ws(const lslb_plan* plan, const LaunchCfg& k, void* ws
   L.pT = take((size_t)plan->Psmall * k.Cpad);
   L.partial = take((size_t)k.nchunks * (plan->Psmall + LSLB_NACC) * k.Cpad);
   L.vsum = take((size_t)2 * k.Cpad);  // residual sums of the (at most two) centring rows
+  L.qf = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
+  off += align_up((size_t)(plan->Psmall + 1) * k.Cpad * sizeof(double), 256);
   L.gtiles = 0;
   L.bT = L.gbT = L.gpl = nullptr;
   if (plan->grp >= 0) {
@@ -712,13 +730,7 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   ep.bT = L.bT;
   ep.gbT = L.gbT;
 
-  {
-    long long total = (long long)plan->Psmall * k.Cpad;
-    if (total > 0) {
-      gather_small_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fp, params, L.pT);
-      LSLB_LAUNCH_CHECK();
-    }
-  }
+  if (int gst = launch_gather_small<T>(fp, params, L.pT, stream)) return gst;
   int G = 0;
   if (plan->grp >= 0) {
     const lslb_block_desc& d = plan->blk[plan->grp];
@@ -756,15 +768,20 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   debug_record_stop(stream);
   if (st != LSLB_OK) return st;
 
-  if (g) {
-    dim3 fgrid(k.Cpad / 32, plan->Psmall + 1);
-    if ((long long)fgrid.x * fgrid.y < 4LL * plan->sm_count)
-      finalize_all_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum,
-                                                                     L.gpl, L.gtiles, G, logp);
+  {
+    // rows: 8 helpers per chain for wide launches, 32 when the grid would leave most SMs idle
+    dim3 fgrid(k.Cpad / 32, plan->Psmall + 1);  // last slice: the log-likelihood
+    T* gout = g ? grad : nullptr;
+    if ((long long)fgrid.x * fgrid.y >= 4LL * plan->sm_count)
+      finalize_rows_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf);
     else
-      finalize_all_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, grad, L.vsum,
-                                                                   L.gpl, L.gtiles, G, logp);
+      finalize_rows_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf);
     LSLB_LAUNCH_CHECK();
+    finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
+                                                                          L.gpl, L.gtiles, G, L.qf, logp);
+    LSLB_LAUNCH_CHECK();
+  }
+  if (g) {
     if (plan->Psmall > plan->Preal) {
       dim3 cgrid((C + 127) / 128, plan->desc.nblocks);
       center_fix_kernel<T><<<cgrid, 128, 0, stream>>>(fp, L.vsum, grad);
@@ -776,10 +793,6 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
                                                           C, k.Cpad, grad);
       LSLB_LAUNCH_CHECK();
     }
-  } else {
-    finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
-                                                                          L.gpl, L.gtiles, G, logp);
-    LSLB_LAUNCH_CHECK();
   }
   return LSLB_OK;
 }

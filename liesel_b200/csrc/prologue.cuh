@@ -7,26 +7,44 @@ namespace lslb {
 // =======================================================================================
 // gather / scatter helpers
 // =======================================================================================
+// params [C x P] -> pT [Psmall x Cpad] (coefficient-major, chains contiguous). Blocks below nb_real: one
+// thread per (real row, chain). Blocks from nb_real on: the VIRTUAL rows (minus the centring term
+// cbar . beta of every centred block of a predictor), one warp per (virtual row, chain) with the lanes
+// over the coefficients - coalesced loads and a fixed shuffle tree instead of a serial chain of
+// ncoef x nblocks dependent double FMAs on strided loads (12 us at the S2 size).
 template <typename T>
 __global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
-                                    const T* __restrict__ params, T* __restrict__ pT) {
+                                    const T* __restrict__ params, T* __restrict__ pT, int nb_real) {
+  if ((int)blockIdx.x >= nb_real) {
+    const int wpb = blockDim.x >> 5;
+    const int per_v = (fp.Cpad + wpb - 1) / wpb;  // blocks per virtual row
+    const int vb = blockIdx.x - nb_real;
+    const int j = fp.Preal + vb / per_v;
+    const int c = (vb % per_v) * wpb + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= fp.Cpad || j >= fp.Psmall) return;
+    double acc = 0.0;
+    if (c < fp.C) {
+      for (int b = 0; b < fp.nblocks; ++b) {
+        const PriorP& pr = fp.pr[b];
+        if (pr.vrow != j) continue;
+        const T* cb = reinterpret_cast<const T*>(pr.center);
+        const T* x = params + (long long)c * fp.P + pr.off;
+        for (int t = lane; t < pr.ncoef; t += 32) acc += (double)cb[t] * (double)x[t];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) pT[(long long)j * fp.Cpad + c] = (T)(-acc);
+    return;
+  }
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)fp.Psmall * fp.Cpad;
+  long long total = (long long)fp.Preal * fp.Cpad;
   if (idx >= total) return;
   int c = (int)(idx % fp.Cpad);
   int j = (int)(idx / fp.Cpad);
   T v = T(0);
-  if (c < fp.C && j >= fp.Preal) {  // virtual row: minus the centring terms of this predictor
-    double acc = 0.0;
-    for (int b = 0; b < fp.nblocks; ++b) {
-      const PriorP& pr = fp.pr[b];
-      if (pr.vrow != j) continue;
-      const T* cb = reinterpret_cast<const T*>(pr.center);
-      const T* x = params + (long long)c * fp.P + pr.off;
-      for (int t = 0; t < pr.ncoef; ++t) acc += (double)cb[t] * (double)x[t];
-    }
-    v = (T)(-acc);
-  } else if (c < fp.C) {
+  if (c < fp.C) {
     for (int b = 0; b < fp.nblocks; ++b) {
       const PriorP& pr = fp.pr[b];
       if (pr.soff >= 0 && j >= pr.soff && j < pr.soff + pr.ncoef) {
@@ -36,6 +54,19 @@ __global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
     }
   }
   pT[idx] = v;
+}
+
+template <typename T>
+inline int launch_gather_small(const FinalizeParams& fp, const T* params, T* pT, cudaStream_t stream) {
+  const long long total = (long long)fp.Preal * fp.Cpad;
+  const int nb_real = (int)((total + 255) / 256);
+  const int nv = fp.Psmall - fp.Preal;
+  const int nb = nb_real + nv * ((fp.Cpad + 7) / 8);
+  if (nb > 0) {
+    gather_small_kernel<T><<<(unsigned)nb, 256, 0, stream>>>(fp, params, pT, nb_real);
+    LSLB_LAUNCH_CHECK();
+  }
+  return LSLB_OK;
 }
 
 // params[:, goff:goff+G] ([C x G] view, row stride P)  ->  bT [G x Cpad]; also initialises the
