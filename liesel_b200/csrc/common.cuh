@@ -229,6 +229,13 @@ struct lslb_plan {
   float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
   float* d_tw[LSLB_MAX_SPL];   // float32 banded plans: per 128-row tile the column sums of each smooth's weights
   float* d_wp[LSLB_MAX_SPL];   // float32 banded Normal plans: per row the products w_a w_b of each smooth ([n][12])
+  // chunk-sorted multi-smooth path (msort_x2.cu): per smooth the weights and local rows of every sub-chunk
+  // in span-sorted order, the run offsets per (sub-chunk, smooth), the sub-chunk boundaries
+  float* d_ms_w[LSLB_MAX_SPL];
+  unsigned short* d_ms_idx[LSLB_MAX_SPL];
+  int* d_ms_off;
+  long long* d_ms_start;
+  int ms_nsub;  // 0: path not prepared
   long long n_pad;
   bool tc_two_pass;  // tensor-core path: two TF32 passes per product are enough for this data (plan-time check)
   int variant;
@@ -281,6 +288,12 @@ bool dense_x2_eligible(const lslb_plan* plan);  // dense_x2.cu
 BandedCfg dense_x2_cfg(const lslb_plan* plan, int C);
 int launch_dense_x2(const lslb_plan* plan, const EvalParams<float>& ep, const BandedCfg& k,
                     bool want_grad, cudaStream_t st);
+int msort_prepare(lslb_plan* plan);  // msort_x2.cu (called by lslb_plan_create)
+void msort_release(lslb_plan* plan);
+bool msort_x2_eligible(const lslb_plan* plan);
+LaunchCfg msort_x2_cfg(const lslb_plan* plan, int C);
+int launch_msort_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k, bool g,
+                    cudaStream_t st);
 bool msmooth_x2_eligible(const lslb_plan* plan);  // msmooth_x2.cu
 LaunchCfg msmooth_x2_cfg(const lslb_plan* plan, int C);
 int launch_msmooth_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k,

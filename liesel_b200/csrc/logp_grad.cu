@@ -523,6 +523,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
   }
   const bool dense = dense_x2_eligible(plan);
   if (!dense && dgroup_x2_eligible(plan)) return dgroup_x2_cfg(plan, C);
+  if (!dense && msort_x2_eligible(plan)) return msort_x2_cfg(plan, C);
   if (!dense && msmooth_x2_eligible(plan)) return msmooth_x2_cfg(plan, C);
   if (dense || banded_fast_eligible(plan)) {
     BandedCfg b = dense ? dense_x2_cfg(plan, C) : banded_cfg(plan, C);
@@ -712,10 +713,11 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   const bool tcp = dense_tc_eligible(plan, C);
   const bool dense = !tcp && dense_x2_eligible(plan);
   const bool dgrp = !tcp && !dense && dgroup_x2_eligible(plan);
-  const bool msm = !tcp && !dense && !dgrp && msmooth_x2_eligible(plan);
-  const bool fast = !tcp && !dense && !dgrp && !msm && banded_fast_eligible(plan);
+  const bool msr = !tcp && !dense && !dgrp && msort_x2_eligible(plan);
+  const bool msm = !tcp && !dense && !dgrp && !msr && msmooth_x2_eligible(plan);
+  const bool fast = !tcp && !dense && !dgrp && !msm && !msr && banded_fast_eligible(plan);
   LaunchCfg k = eval_cfg(plan, C);
-  size_t smem = (fast || dense || dgrp || tcp || msm) ? 0 : eval_smem_per_chain(plan) * k.TC + eval_smem_fixed(plan);
+  size_t smem = (fast || dense || dgrp || tcp || msm || msr) ? 0 : eval_smem_per_chain(plan) * k.TC + eval_smem_fixed(plan);
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
   if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
@@ -754,6 +756,8 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
     if constexpr (sizeof(T) == 4) st = launch_dense_x2(plan, ep, dense_x2_cfg(plan, C), g, stream);
   } else if (dgrp) {
     if constexpr (sizeof(T) == 4) st = launch_dgroup_x2(plan, ep, k, g, stream);
+  } else if (msr) {
+    if constexpr (sizeof(T) == 4) st = launch_msort_x2(plan, ep, k, g, stream);
   } else if (msm) {
     if constexpr (sizeof(T) == 4) st = launch_msmooth_x2(plan, ep, k, g, stream);
   } else if (fast) {
@@ -810,6 +814,7 @@ extern "C" const char* lslb_plan_kernel_name(const lslb_plan* plan, int C) {
   if (dense_tc_eligible(plan, C)) return "lslb::dense_tc_k1 + lslb::dense_tc_k2";
   if (dense_x2_eligible(plan)) return "lslb::dense_x2_kernel";
   if (dgroup_x2_eligible(plan)) return "lslb::dgroup_x2_kernel";
+  if (msort_x2_eligible(plan)) return "lslb::msort_x2_kernel";
   if (msmooth_x2_eligible(plan)) return "lslb::msmooth_x2_kernel";
   if (banded_fast_eligible(plan))
     return banded_cfg(plan, C).TC == 256 ? "lslb::banded_x2_kernel" : "lslb::banded_kernel";

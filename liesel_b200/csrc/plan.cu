@@ -357,6 +357,13 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   }
   dense_tc_prepare(p);
   if (p->d_XT) p->variant_name = "dense_tcgen05_tf32x3";
+  if (p->variant == VAR_BANDED) {
+    if (msort_prepare(p) != LSLB_OK) {
+      lslb_plan_destroy(p);
+      return LSLB_ERR_CUDA;
+    }
+    if (msort_x2_eligible(p)) p->variant_name = "multi_smooth_chunk_sorted_x2";
+  }
   if (p->variant == VAR_BANDED && desc->dtype == LSLB_F32 && n > 0) {
     const long long ntiles = (n + 127) / 128;
     for (int m = 0; m < p->ns && e == cudaSuccess; ++m) {
@@ -396,6 +403,7 @@ extern "C" void lslb_plan_destroy(lslb_plan* p) {
   for (int m = 0; m < LSLB_MAX_SPL; ++m)
     if (p->d_wp[m]) cudaFree(p->d_wp[m]);
   lslb::dense_tc_release(p);
+  lslb::msort_release(p);
   delete p;
 }
 
