@@ -1,6 +1,13 @@
 // Several P-splines of DIFFERENT covariates, few chains (S2: 5 cubic smooths x 20 coefficients,
-// n = 1e5, 64 chains; float32) - the chunk-sorted kernel (round 2; msmooth_x2.cu is its predecessor
-// and stays as the fallback, LSLB_NO_MSORT=1).
+// n = 1e5, 64 chains; float32) - the chunk-sorted kernel (round 2). EXPERIMENT, OFF BY DEFAULT
+// (LSLB_MSORT=1 switches it on at plan creation): parity-green on the GPU (all S2 / family / centring
+// tests, BASELINE-size S2 against the fp64 oracle) but SLOWER than msmooth_x2.cu at S2 - 122 us
+// against 90 us (profiles/r02_s2_msort_full.md): 12.5 instructions per row, smooth and direction as
+// designed, but the walk is a serial chain global load (local row) -> shared load (eta) -> FMA ->
+// shared store with no overlap between iterations, runs of ~5 rows per warp segment, and 17
+// barriers per 169-row sub-chunk; 16 warps issue 33 % of the time (long-scoreboard 3.5, barrier 2.2,
+// wait 2.3 stall cycles per issued instruction). Kept in-tree because it removes the indirect branch
+// and is the base for a version with the sorted rows staged in shared memory; see DESIGN.md section 4.
 //
 // What was wrong with msmooth_x2 (ncu, profiles/r02_s2_msmooth_full.md): a warp kept one smooth's 20
 // coefficients and 20 gradient accumulators in registers and reached them through `switch (span)` -
@@ -321,8 +328,8 @@ static bool msort_structurally_ok(const lslb_plan* plan) {
 // called by lslb_plan_create once the variant is known
 int msort_prepare(lslb_plan* plan) {
   plan->ms_nsub = 0;
-  const char* e = getenv("LSLB_NO_MSORT");
-  if (e && atoi(e) != 0) return LSLB_OK;
+  const char* e = getenv("LSLB_MSORT");
+  if (!(e && atoi(e) != 0)) return LSLB_OK;  // opt-in experiment (see the header)
   if (!msort_structurally_ok(plan) || banded_fast_eligible(plan)) return LSLB_OK;
   const long long n = plan->desc.n;
   const int want = (int)((n + MSR_SC - 1) / MSR_SC);
