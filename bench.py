@@ -58,9 +58,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the per-config / sharded entries")
     ap.add_argument("--no-ess", action="store_true", help="skip the NUTS ESS/sec run")
-    # ESS run sized for the bench budget (~2 min on the GPU): 256 chains; the 1024-chain run of the
-    # metric (--ess-chains 1024 --ess-warmup 500 --ess-term 250) takes ~5 min and is committed under profiles/
-    ap.add_argument("--ess-chains", type=int, default=256)
+    # ESS run sized for the bench budget (~2 min on the GPU): 512 chains; the 1024-chain run of the
+    # metric (--ess-chains 1024) takes ~3.5 min and is committed under profiles/
+    ap.add_argument("--ess-chains", type=int, default=512)
+    ap.add_argument("--ess-driver", default="async", choices=["async", "lockstep"])
     ap.add_argument("--ess-warmup", type=int, default=650, help="warm-up duration (Stan-style epochs, goose/warmup.py)")
     ap.add_argument("--ess-term", type=int, default=500,
                     help="length of the final fast-adaptation epoch (reference default 50; its own kernel tests "
@@ -400,9 +401,11 @@ def run_ess(args, torch, dev, plan, spec, centre, local):
     """NUTS-within-Gibbs on H: all coefficients in one NUTS block (reference NUTSKernel defaults:
     max_treedepth 10, target acceptance 0.8, diagonal mass matrix, Stan-style warm-up epochs), tau2
     by its Gibbs full conditional after every transition; both smooths under the sum-to-zero
-    constraint (liesel_b200/reparam.py). ESS = min over coordinates of bulk-ESS of all posterior draws."""
+    constraint (liesel_b200/reparam.py). ESS = min over coordinates of bulk-ESS of all posterior draws.
+    Driver: the asynchronous one (liesel_b200/nuts_async.py: every chain walks its own trees, the batch
+    shares one evaluation per step) unless --ess-driver lockstep."""
     from liesel_b200 import reparam, synth
-    from liesel_b200.nuts_gibbs import NutsGibbs, PlanEvaluator, summarise
+    from liesel_b200.nuts_gibbs import AsyncNutsGibbs, NutsGibbs, PlanEvaluator, summarise, summarise_async
 
     C, W, S = args.ess_chains, args.ess_warmup, args.ess_samples
     cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
@@ -410,30 +413,48 @@ def run_ess(args, torch, dev, plan, spec, centre, local):
     th0, aux0 = synth.evaluation_points(spec, centre, C, seed=1)
     sampler = ClockSampler(local)
     sampler.wait_started()
-    t0 = time.perf_counter()
-    run = NutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev),
-                    torch.as_tensor(aux0, device=dev), reparam=rep, seed=1, compact=True)
-    winfo = run.warmup(W, term_duration=args.ess_term)
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    draws, infos = run.sample(S)
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    clocks = sampler.stop()
-    out = summarise(draws, infos, t2 - t1, t1 - t0)
-    nuts = run.nuts
+    common = ("one NUTS block over all coefficients + Gibbs draw of every tau2 per transition; reference "
+              "defaults (max_treedepth 10, target accept 0.8, diagonal mass matrix, Stan-style warm-up epochs "
+              f"with a final fast epoch of {args.ess_term}); ")
+    if args.ess_driver == "async":
+        run = AsyncNutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev),
+                             torch.as_tensor(aux0, device=dev), W, S, reparam=rep, seed=1,
+                             epoch_kw=dict(term_duration=args.ess_term))
+        timing = run.run()
+        clocks = sampler.stop()
+        out = summarise_async(run, timing)
+        q_state, step_state, mass_state = run.nuts.st["q"], run.nuts.st["step"], run.nuts.st["inv_mass"]
+        out.update({
+            "sampler": common + "asynchronous driver: every chain walks its own trees, one batched evaluation "
+                                "per step shared by all chains (lslb_nuts_async_step)",
+            "mean_batch_fill": 1.0,
+        })
+    else:
+        t0 = time.perf_counter()
+        run = NutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev),
+                        torch.as_tensor(aux0, device=dev), reparam=rep, seed=1, compact=True)
+        winfo = run.warmup(W, term_duration=args.ess_term)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        draws, infos = run.sample(S)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        clocks = sampler.stop()
+        out = summarise(draws, infos, t2 - t1, t1 - t0)
+        nuts = run.nuts
+        q_state, step_state, mass_state = nuts.q, nuts.step_size, nuts.inv_mass
+        out.update({
+            "sampler": common + "lock-step driver, finished chains dropped from the batched evaluation",
+            "warmup_mean_treedepth": float(np.mean([float(i.treedepth.float().mean()) for i in winfo])),
+            "batched_evals_warmup": int(sum(i.evaluations for i in winfo)),
+            "step_size_median": float(nuts.step_size.median()),
+            "mean_batch_fill": float(nuts.chain_evals) / max(1.0, float(nuts.evals) * C),
+        })
     out.update({
-        "sampler": ("one NUTS block over all coefficients + Gibbs draw of every tau2 per transition; "
-                    "reference defaults (max_treedepth 10, target accept 0.8, diagonal mass matrix, "
-                    f"Stan-style warm-up epochs with a final fast epoch of {args.ess_term}), finished chains "
-                    "dropped from the batched evaluation"),
+        "driver": args.ess_driver,
         "model": workload_name(spec.n, C).replace(" per GPU", ""),
         "constraint": "sum-to-zero on both smooths (beta = Z gamma, 2 x 19 + 2 = 40 sampled coordinates)",
         "warmup_iters": W, "warmup_term_duration": args.ess_term, "posterior_iters": S,
-        "warmup_mean_treedepth": float(np.mean([float(i.treedepth.float().mean()) for i in winfo])),
-        "batched_evals_warmup": int(sum(i.evaluations for i in winfo)),
-        "step_size_median": float(nuts.step_size.median()),
-        "mean_batch_fill": float(nuts.chain_evals) / max(1.0, float(nuts.evals) * C),
         "clocks": clocks,
     })
     # ---- CPU arm: the same sampler on the oracle's CPU port, host cores ----------------------
@@ -445,12 +466,12 @@ def run_ess(args, torch, dev, plan, spec, centre, local):
         torch.set_num_threads(os.cpu_count() or 1)
         ev = CpuEvaluator(spec)
         rep_c = reparam.sum_to_zero(spec, cm)
-        q_full = run.full(nuts.q[:Cc]).cpu()
+        q_full = run.full(q_state[:Cc]).cpu()
         run_c = NutsGibbs(spec, ev, q_full, run.aux[:Cc].cpu(), reparam=rep_c, seed=2,
                           initial_step_size=1.0, fused=False)
         # adapted state of the GPU run's first Cc chains: the CPU arm times POSTERIOR transitions
-        run_c.nuts.step_size = nuts.step_size[:Cc].cpu().clone()
-        run_c.nuts.inv_mass = nuts.inv_mass[:Cc].cpu().clone()
+        run_c.nuts.step_size = step_state[:Cc].cpu().clone()
+        run_c.nuts.inv_mass = mass_state[:Cc].cpu().clone()
         ev0 = run_c.nuts.evals
         tc0 = time.perf_counter()
         iters = 0
@@ -465,7 +486,7 @@ def run_ess(args, torch, dev, plan, spec, centre, local):
             "seconds": dtc, "seconds_per_transition": dtc / iters,
             "batched_evals": int(run_c.nuts.evals - ev0),
             "ess_per_sec_posterior": ess_per_draw_chain * Cc * iters / dtc,
-            "how": ("real NUTS+Gibbs transitions on oracle/cpu_port.py (torch CPU fp32, all host threads) from "
+            "how": ("real lock-step NUTS+Gibbs transitions on oracle/cpu_port.py (torch CPU fp32, all host threads) from "
                     "the GPU run's adapted state (positions, step sizes, mass matrices of its first "
                     f"{Cc} chains); ESS per draw and chain ({ess_per_draw_chain:.3f}) is the GPU run's — same "
                     "sampler, same model — because a CPU run long enough to estimate ESS itself does not "

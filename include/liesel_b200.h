@@ -326,6 +326,20 @@ int lslb_nuts_leaf_post_f32(void* const* ptrs, const int* ints, double div_thr, 
 int lslb_nuts_leaf_post_f64(void* const* ptrs, const int* ints, double div_thr, lslb_stream_t stream);
 
 /*
+ * State machine of the asynchronous batched NUTS driver (liesel_b200/nuts_async.py; f1 of SURVEY 8):
+ * one launch between two batched log-posterior+gradient evaluations, one warp per chain. Every chain
+ * walks its own tree (BlackJAX iterative NUTS as driven by goose/nuts.py:240-264), ends its transition
+ * with dual averaging (goose/da.py:69-127), the mass-matrix window sums / epoch ends (goose/mm.py:19-35,
+ * goose/warmup.py:12-88), the draw and optionally the Gibbs update of smoothing variances
+ * (model/distreg.py:277-297), and starts the next one in the same launch; the evaluation at q_n
+ * (ptrs[29]) is the caller's. ptrs: 58 device pointers in the order of csrc/nuts_async.cu's NutsAsync;
+ * ints = {C, P, max_treedepth + 1, max_treedepth, warmup, samples, epochs, gibbs blocks, A};
+ * dbls = {divergence threshold, target accept, gamma, kappa, t0}. The random numbers of a step are inputs.
+ */
+int lslb_nuts_async_step_f32(void* const* ptrs, const int* ints, const double* dbls, lslb_stream_t stream);
+int lslb_nuts_async_step_f64(void* const* ptrs, const int* ints, const double* dbls, lslb_stream_t stream);
+
+/*
  * Measurement hook (used by bench.py; no effect on results).
  * lslb_debug_set_events: the given cudaEvent_t pair is recorded on the call's stream immediately
  *   before and after the dominant row-streaming kernel of every following lslb_logp_grad_* /

@@ -136,6 +136,9 @@ for _sfx in ("f32", "f64"):
     f = getattr(lib, "lslb_nuts_leaf_post_" + _sfx)
     f.restype = _i
     f.argtypes = [C.POINTER(_vp), C.POINTER(_i), C.c_double, _vp]
+    f = getattr(lib, "lslb_nuts_async_step_" + _sfx)
+    f.restype = _i
+    f.argtypes = [C.POINTER(_vp), C.POINTER(_i), C.POINTER(C.c_double), _vp]
 
 lib.lslb_debug_set_events.restype = _i
 lib.lslb_debug_set_events.argtypes = [_vp, _vp]
@@ -166,6 +169,7 @@ EXPORTS = [
     "lslb_logp_grad_nccl_f32", "lslb_logp_grad_nccl_f64", "lslb_iwls_nccl_f32", "lslb_iwls_nccl_f64",
     "lslb_debug_set_events", "lslb_debug_event_count",
     "lslb_nuts_leaf_pre_f32", "lslb_nuts_leaf_pre_f64", "lslb_nuts_leaf_post_f32", "lslb_nuts_leaf_post_f64",
+    "lslb_nuts_async_step_f32", "lslb_nuts_async_step_f64",
     "lslb_version", "lslb_status_string", "lslb_last_cuda_error", "lslb_plan_create",
     "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_dtype", "lslb_plan_block_ncoef", "lslb_plan_variant", "lslb_plan_kernel_name",
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",

@@ -103,6 +103,89 @@ class NutsGibbs:
         return self.nuts.sample(num_samples, hook=self._gibbs)
 
 
+class AsyncNutsGibbs:
+    """The same sampling scheme on the asynchronous driver (``nuts_async.AsyncNUTS``): every chain runs
+    its own trees and its own Gibbs updates, the batch shares one evaluation per step. The Gibbs blocks
+    are handed to the driver in the SAMPLER's coordinates: ``beta' K beta = gamma' (T_b' K T_b) gamma``
+    with ``T_b`` the block's rows of the reparametrisation (identity rows without one)."""
+
+    def __init__(self, spec, evaluator, q0: torch.Tensor, aux0: torch.Tensor | None, warmup: int, samples: int,
+                 reparam=None, seed: int = 0, backend: str | None = None, epoch_kw: dict | None = None, **nuts_kw):
+        from .nuts_async import AsyncNUTS
+
+        self.spec, self.ev, self.rep = spec, evaluator, reparam
+        self.C = q0.shape[0]
+        self.dev, self.dt = q0.device, q0.dtype
+        self.aux = None if aux0 is None else aux0.clone().contiguous()
+        self._full_q = torch.empty_like(q0)
+        self._full_g = torch.empty_like(q0)
+        self._out_ok = bool(q0.is_cuda)
+        start = (q0 if reparam is None else reparam.reduce(q0)).contiguous()
+        Pr = start.shape[1]
+        T = (torch.eye(q0.shape[1], dtype=torch.float64) if reparam is None
+             else reparam.T.detach().double().cpu())
+        gibbs = []
+        for b in spec.blocks:
+            if b.tau2_slot < 0 or b.prior.ig_a is None:
+                continue
+            K = torch.as_tensor(np.asarray(b.prior.K), dtype=torch.float64)
+            Tb = T[b.param_offset: b.param_offset + b.ncoef, :]
+            gibbs.append(dict(M=Tb.t() @ K @ Tb, b0=float(b.prior.ig_b),
+                              a_post=float(b.prior.ig_a) + 0.5 * float(b.prior.rank), slot=int(b.tau2_slot)))
+        assert all(g["M"].shape == (Pr, Pr) for g in gibbs)
+        self.nuts = AsyncNUTS(self._f_into, start, warmup, samples, seed=seed, aux=self.aux, gibbs=gibbs,
+                              backend=backend, epoch_kw=epoch_kw, **nuts_kw)
+
+    def full(self, q_r: torch.Tensor) -> torch.Tensor:
+        return q_r if self.rep is None else self.rep.expand(q_r)
+
+    def _f_into(self, q_r, lp, g_r):
+        if self.rep is None:
+            qf, gf = q_r, g_r
+        else:
+            qf, gf = self._full_q, self._full_g
+            self.rep.expand(q_r, out=qf)
+        if self._out_ok:
+            self.ev.logp_grad(qf, self.aux, out=(lp, gf))
+        else:
+            l, g = self.ev.logp_grad(qf, self.aux)
+            lp.copy_(l)
+            gf.copy_(g)
+        if self.rep is not None:
+            self.rep.reduce_grad(gf, out=g_r)
+
+    def run(self, **kw) -> dict:
+        return self.nuts.run(**kw)
+
+    def draws(self) -> torch.Tensor:
+        return self.nuts.draws()
+
+
+def summarise_async(run: "AsyncNutsGibbs", timing: dict) -> dict:
+    """The columns of :func:`summarise` for an asynchronous run."""
+    from . import diagnostics
+
+    d = run.draws()
+    t0 = time.perf_counter()
+    ess = diagnostics.ess_bulk_device(d)
+    rhat = diagnostics.split_rhat_device(d)
+    sm = run.nuts.summary()
+    sp, sw = timing["seconds_posterior"], timing["seconds_warmup"]
+    return {
+        "ess_bulk_min": float(np.min(ess)), "ess_bulk_median": float(np.median(ess)),
+        "split_rhat_max": float(np.max(rhat)),
+        "draws": int(d.shape[0]), "chains": int(d.shape[1]), "coordinates": int(d.shape[2]),
+        "posterior_seconds": sp, "ess_per_sec_posterior": float(np.min(ess) / sp),
+        "mean_accept": sm["mean_accept"], "mean_treedepth": sm["mean_treedepth"],
+        "divergent_frac": sm["divergent_frac"], "mean_leapfrogs": sm["mean_leapfrogs"],
+        "batched_evals_posterior": int(timing["steps_posterior"]),
+        "batched_evals_warmup": int(timing["steps_warmup"]),
+        "diagnostics_seconds": time.perf_counter() - t0,
+        "warmup_seconds": sw, "ess_per_sec_incl_warmup": float(np.min(ess) / (sp + sw)),
+        "step_size_median": sm["step_size_median"],
+    }
+
+
 def summarise(draws: torch.Tensor, infos, seconds_posterior: float, seconds_warmup: float | None = None) -> dict:
     """Bulk-ESS / split-R-hat of all coordinates (``goose/summary_m.py:756-760`` columns) + sampler
     statistics; ``draws [S, C, P]`` stay on their device."""

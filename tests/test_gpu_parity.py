@@ -1027,6 +1027,140 @@ def test_nuts_gibbs_on_device_converges(lb):
     np.testing.assert_allclose(fit, 1.0 + np.sin(2 * np.pi * xs), atol=0.05)
 
 
+# --- asynchronous NUTS driver: the CUDA state machine against its torch statement --------------------------
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_nuts_async_kernel_matches_torch_statement_step_by_step(dtype):
+    """``lslb_nuts_async_step`` against ``AsyncNUTS._step_torch`` on the same device, same state, same
+    random inputs, step after step through warm-up epochs (dual averaging, mass-matrix windows), Gibbs
+    updates of an auxiliary scale, draws: integer state identical, floats to rounding. (Random numbers
+    are inputs of a step, so the comparison is deterministic.) The two states are re-synchronised after
+    every comparison so that a last-bit difference cannot grow and flip a later accept decision."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from liesel_b200.nuts_async import AsyncNUTS
+
+    C, P = 48, 7
+    d = torch.device("cuda")
+    scale = torch.linspace(0.5, 3.0, P, device=d, dtype=dtype)
+    M = torch.diag(1.0 / scale).to(dtype)
+
+    def make(backend):
+        aux = torch.ones((C, 2), dtype=dtype, device=d)
+
+        def f_into(q, lp, g):  # N(0, tau2 * diag(scale)) with tau2 = aux[:, 1]
+            t = aux[:, 1:2]
+            lp.copy_((-0.5 * q * q / (scale * t)).sum(dim=1) - 0.5 * P * torch.log(t[:, 0]))
+            g.copy_(-q / (scale * t))
+
+        q0 = torch.linspace(-1, 1, C * P, device=d, dtype=dtype).reshape(C, P).contiguous()
+        gib = [dict(M=M, b0=1.5, a_post=2.0 + 0.5 * P, slot=1)]
+        return AsyncNUTS(f_into, q0, warmup=60, samples=25, seed=3, aux=aux, gibbs=gib, backend=backend,
+                         initial_step_size=0.3, max_treedepth=5,
+                         epoch_kw=dict(init_duration=15, term_duration=15, base_duration=10))
+
+    A, B = make("torch"), make("cuda")
+    keys_f = ["q", "lp", "g", "step", "inv_mass", "h0", "qp", "lpp", "log_w", "rsum", "qe", "re", "ge", "qs", "logw_s",
+              "rsum_s", "qn", "r_half", "da_err", "da_logavg", "da_mu", "sum_acc", "n_leaf"]
+    keys_i = ["phase", "depth", "dir", "i_leaf", "n_leaves", "it", "ep", "t_ep", "flags"]
+    tol = 1e-11 if dtype == torch.float64 else 2e-5
+    for stage, S_act in (("warmup", 0), ("posterior", 25)):
+        for X in (A, B):
+            X._active_S = S_act
+            X._ptrs = None
+            X.st["phase"].fill_(0)
+            X.st["n_done"].zero_()
+            X.st["qn"].copy_(X.st["q"])
+            X._evaluate()
+        for step in range(6000):
+            A._randoms()
+            B._Z.copy_(A._Z); B._U.copy_(A._U); B._G.copy_(A._G)
+            A._step(); B._step()
+            for k in keys_i:
+                assert torch.equal(A.st[k], B.st[k]), (stage, step, k)
+            leaf = A.st["phase"] == 1
+            for k in keys_f:
+                a, b = A.st[k].double(), B.st[k].double()
+                if k == "r_half":  # scratch outside a leaf (the kernel parks r_n there)
+                    a, b = a[leaf], b[leaf]
+                fin = torch.isfinite(a)
+                assert torch.equal(fin, torch.isfinite(b)), (stage, step, k)
+                err = ((a - b).abs() / (1.0 + a.abs()))[fin]
+                assert err.numel() == 0 or float(err.max()) < tol, (stage, step, k, float(err.max()))
+            assert torch.allclose(A.aux.double(), B.aux.double(), rtol=tol * 10, atol=0)
+            # re-synchronise: Hamiltonian trajectories amplify a last-bit difference exponentially (1e-11
+            # after 128 steps in float64), and an accept decision would eventually flip
+            if True:
+                for k in keys_f + ["gs", "gp", "qL", "rL", "gL", "qR", "rR", "gR", "lps", "ck_r", "ck_s", "ws1", "ws2"]:
+                    B.st[k].copy_(A.st[k])
+                B.aux.copy_(A.aux)
+            A._evaluate(); B._evaluate()
+            if int(A.st["n_done"].item()) >= C:
+                assert int(B.st["n_done"].item()) >= C
+                break
+        else:
+            raise AssertionError("stage did not finish")
+    assert torch.allclose(A.draws().double(), B.draws().double(), rtol=tol * 10, atol=tol * 10)
+    assert torch.allclose(A.st["stats"], B.st["stats"], rtol=1e-6, atol=1e-6)
+    assert int(A.st["it"].min()) == 85
+
+
+def test_nuts_async_on_device_recovers_model_lm(lb, golden_dir):
+    """The reference's kernel integration pins (``model_lm.py:70-84``) with the asynchronous driver on
+    the GPU: CUDA log-prob/gradient through the C ABI + the state-machine kernel."""
+    from liesel_b200.nuts_async import AsyncNUTS
+
+    g, plan = _model_lm_plan(lb, golden_dir)
+    C = 64
+    q0 = torch.tensor([g["beta"] + [g["log_sigma"]]], dtype=torch.float64, device="cuda").repeat(C, 1)
+
+    def f_into(q, lp, gr):
+        plan.logp_grad(q, None, out=(lp, gr))
+
+    s = AsyncNUTS(f_into, q0, warmup=2000, samples=400, seed=42, epoch_kw=dict(term_duration=1500))
+    assert s.backend == "cuda"
+    t = s.run()
+    d = s.draws().cpu().numpy()
+    assert d[:, :, :2].mean(axis=(0, 1)) == pytest.approx(np.array(g["beta_ols"]), rel=0.05)
+    assert d[:, :, 2].mean() == pytest.approx(np.log(g["sigma_ols"]), rel=0.05)
+    sm = s.summary()
+    assert sm["mean_accept"] == pytest.approx(0.8, abs=0.05), sm
+    assert sm["divergent_frac"] < 0.02
+    from liesel_b200 import diagnostics
+
+    assert diagnostics.split_rhat_device(s.draws()).max() < 1.02
+    # the batch stays full: sequential evaluations ~ transitions x mean leapfrogs, not x deepest tree
+    assert t["steps_warmup"] + t["steps_posterior"] < 2400 * 16
+
+
+def test_async_nuts_gibbs_on_device_converges(lb):
+    """The ESS metric's sampling scheme on the asynchronous driver at a reduced H (see
+    ``test_nuts_gibbs_on_device_converges`` for the lock-step counterpart)."""
+    from liesel_b200 import reparam
+    from liesel_b200.nuts_gibbs import AsyncNutsGibbs, PlanEvaluator, summarise_async
+
+    spec, centre = synth.s3_gamlss(n=50_000)
+    plan = lb.Plan(spec)
+    cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
+    rep = reparam.sum_to_zero(spec, cm, device=plan.device)
+    C, S = 256, 200
+    th, aux = synth.evaluation_points(spec, centre, C, seed=1)
+    run = AsyncNutsGibbs(spec, PlanEvaluator(plan), dev(th, plan), dev(aux, plan), 300, S, reparam=rep, seed=1)
+    t = run.run()
+    s = summarise_async(run, t)
+    ess_half = s["ess_bulk_min"] / (2 * C)
+    assert s["split_rhat_max"] < np.sqrt(1.0 + 2.0 / ess_half), s
+    assert s["ess_bulk_min"] > 0.05 * C * S, s
+    assert s["divergent_frac"] < 0.01 and s["mean_treedepth"] < 7, s
+    q = run.full(run.draws().reshape(-1, run.draws().shape[2])).double().mean(dim=0).cpu().numpy()
+    from oracle import splines as OSp
+
+    xs = np.linspace(0.05, 0.95, 19)
+    blk = spec.block("loc_np0")
+    B = OSp.basis_matrix(xs, np.asarray(blk.knots, dtype=np.float64), 3)
+    fit = q[0] + B @ q[blk.param_offset: blk.param_offset + blk.ncoef]
+    np.testing.assert_allclose(fit, 1.0 + np.sin(2 * np.pi * xs), atol=0.05)
+
+
 # --- B-spline orders below 3 (contrib/splines.py:109-198 is order-generic) -----------------------------
 @pytest.mark.parametrize("order", [0, 1, 2])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -15,7 +15,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from liesel_b200 import reparam, synth  # noqa: E402
-from liesel_b200.nuts_gibbs import NutsGibbs, PlanEvaluator, summarise  # noqa: E402
+from liesel_b200.nuts_gibbs import AsyncNutsGibbs, NutsGibbs, PlanEvaluator, summarise, summarise_async  # noqa: E402
 from liesel_b200.plan import Plan  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -26,6 +26,8 @@ ap.add_argument("--samples", type=int, default=100)
 ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--no-compact", action="store_true")
 ap.add_argument("--term", type=int, default=50)
+ap.add_argument("--async", dest="use_async", action="store_true",
+                help="asynchronous driver (nuts_async.AsyncNUTS): per-chain trees, the batch shares the evaluation")
 args = ap.parse_args()
 
 spec, centre = synth.s3_gamlss(n=args.n)
@@ -35,6 +37,23 @@ cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
 rep = reparam.sum_to_zero(spec, cm, device=dev)
 C = args.chains
 th0, aux0 = synth.evaluation_points(spec, centre, C, seed=args.seed)
+if args.use_async:
+    run = AsyncNutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev), torch.as_tensor(aux0, device=dev),
+                         args.warmup, args.samples, reparam=rep, seed=args.seed, epoch_kw=dict(term_duration=args.term))
+    timing = run.run()
+    out = summarise_async(run, timing)
+    n = run.nuts
+    W, S = args.warmup, args.samples
+    out.update({
+        "driver": "async", "chains": C, "warmup": W, "samples": S,
+        "ms_per_transition_posterior": 1e3 * timing["seconds_posterior"] / S,
+        "ms_per_transition_warmup": 1e3 * timing["seconds_warmup"] / W,
+        "ms_per_batched_eval": 1e3 * timing["seconds_posterior"] / timing["steps_posterior"],
+        "batched_evals_per_transition": timing["steps_posterior"] / S,
+        "step_size_quantiles": dict(zip(["0", "0.5", "1"], np.quantile(n.st["step"].cpu().numpy(), [0, 0.5, 1]).tolist())),
+    })
+    print(json.dumps(out), flush=True)
+    sys.exit(0)
 run = NutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th0, device=dev), torch.as_tensor(aux0, device=dev),
                 reparam=rep, seed=args.seed, compact=not args.no_compact)
 t0 = time.perf_counter()
