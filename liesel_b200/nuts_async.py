@@ -62,7 +62,7 @@ class AsyncNUTS:
                  max_treedepth: int = 10, da_target_accept: float = 0.8, da_gamma: float = 0.05,
                  da_kappa: float = 0.75, da_t0: int = 10, divergence_threshold: float = 1000.0, seed: int = 0,
                  initial_step_size: float | None = None, aux: torch.Tensor | None = None, gibbs: list | None = None,
-                 backend: str | None = None, epoch_kw: dict | None = None):
+                 backend: str | None = None, epoch_kw: dict | None = None, compact_tail: bool = False):
         """
         ``logp_grad_into(q [C, P], logp_out [C], grad_out [C, P])`` evaluates the batch into the given
         buffers (it may read ``aux``, which this driver updates in place when ``gibbs`` is given).
@@ -70,6 +70,8 @@ class AsyncNUTS:
         transition ``aux[c, slot] = (b0 + q' M q / 2) / Gamma(a_post, 1)`` and the chain re-evaluates
         its position before the next transition.
         ``backend``: "cuda" (kernel; default on CUDA tensors) or "torch" (masked torch ops).
+        ``compact_tail``: ``logp_grad_into`` also accepts ``chains=idx`` (indices of the chains of a
+        gathered batch); chains that finished a stage are then dropped from the evaluation.
         """
         self.f_into = logp_grad_into
         self.C, self.P = q0.shape
@@ -89,6 +91,10 @@ class AsyncNUTS:
         self.ep_kind = torch.tensor([1 if k == "slow" else 0 for k, _ in ep] + [0], dtype=torch.int32, device=self.dev)
         self.nep = len(ep)
         self.steps = 0
+        self.chain_evals = 0
+        self._active_idx = None
+        self.compact_tail = bool(compact_tail)
+        self.compact_below = 0.85
         self._active_S = 0  # posterior draws of the running stage (0 during the warm-up stage)
         self._init_state(q0, initial_step_size, seed)
 
@@ -124,6 +130,7 @@ class AsyncNUTS:
             self.f_into(q.contiguous(), lp, g)
             return lp, g
 
+
         init = BatchedNUTS(f, q0, seed=seed, initial_step_size=initial_step_size, fused=False,
                            da_target_accept=self.target)
         s["step"].copy_(init.step_size)
@@ -156,7 +163,32 @@ class AsyncNUTS:
 
     def _evaluate(self):
         s = self.st
-        self.f_into(s["qn"], s["lp_n"], s["g_n"])
+        idx = self._active_idx
+        if idx is None:
+            self.f_into(s["qn"], s["lp_n"], s["g_n"])
+        else:  # tail of a stage: only the chains that are still running are evaluated
+            n = idx.numel()
+            qc, lpc, gc = self._cq[:n], self._clp[:n], self._cg[:n]
+            torch.index_select(s["qn"], 0, idx, out=qc)
+            self.f_into(qc, lpc, gc, chains=idx)
+            s["lp_n"].index_copy_(0, idx, lpc)
+            s["g_n"].index_copy_(0, idx, gc)
+        self.chain_evals += self.C if idx is None else int(idx.numel())
+
+    def _maybe_compact(self, n_done: int):
+        """Chains finish a stage at different steps (per-chain step sizes give per-chain tree sizes): once
+        a share of them is done, the evaluation runs on the gathered batch of the others (the evaluation
+        kernel's time is proportional to the chains it is given). Needs a callback that accepts ``chains=``."""
+        if not self.compact_tail:
+            return
+        active = self.C - n_done
+        cur = self.C if self._active_idx is None else int(self._active_idx.numel())
+        if active <= self.compact_below * cur and active > 0:
+            self._active_idx = (self.st["phase"] != DONE).nonzero().squeeze(1)
+            if not hasattr(self, "_cq"):
+                self._cq = torch.empty_like(self.st["qn"])
+                self._clp = torch.empty_like(self.st["lp_n"])
+                self._cg = torch.empty_like(self.st["g_n"])
 
     @torch.no_grad()
     def run(self, check_every: int = 64):
@@ -178,6 +210,7 @@ class AsyncNUTS:
             s["phase"].fill_(REFRESH)
             s["n_done"].zero_()
             s["qn"].copy_(s["q"])
+            self._active_idx = None
             sync()
             t0 = time.perf_counter()
             n0 = self.steps
@@ -189,8 +222,10 @@ class AsyncNUTS:
                     self._step()
                     self._evaluate()
                     self.steps += 1
-                if int(s["n_done"].item()) >= self.C:
+                nd = int(s["n_done"].item())
+                if nd >= self.C:
                     break
+                self._maybe_compact(nd)
             sync()
             out["steps_" + stage] = self.steps - n0
             out["seconds_" + stage] = time.perf_counter() - t0

@@ -133,22 +133,29 @@ class AsyncNutsGibbs:
             gibbs.append(dict(M=Tb.t() @ K @ Tb, b0=float(b.prior.ig_b),
                               a_post=float(b.prior.ig_a) + 0.5 * float(b.prior.rank), slot=int(b.tau2_slot)))
         assert all(g["M"].shape == (Pr, Pr) for g in gibbs)
+        nuts_kw.setdefault("compact_tail", True)
         self.nuts = AsyncNUTS(self._f_into, start, warmup, samples, seed=seed, aux=self.aux, gibbs=gibbs,
                               backend=backend, epoch_kw=epoch_kw, **nuts_kw)
 
     def full(self, q_r: torch.Tensor) -> torch.Tensor:
         return q_r if self.rep is None else self.rep.expand(q_r)
 
-    def _f_into(self, q_r, lp, g_r):
+    def _f_into(self, q_r, lp, g_r, chains=None):
+        """``chains``: indices of the chains of a gathered batch (their CURRENT tau2 rows are selected:
+        the Gibbs updates change ``aux`` from step to step)."""
+        n = q_r.shape[0]
+        aux = self.aux
+        if chains is not None and aux is not None:
+            aux = aux.index_select(0, chains)
         if self.rep is None:
             qf, gf = q_r, g_r
         else:
-            qf, gf = self._full_q, self._full_g
+            qf, gf = self._full_q[:n], self._full_g[:n]
             self.rep.expand(q_r, out=qf)
         if self._out_ok:
-            self.ev.logp_grad(qf, self.aux, out=(lp, gf))
+            self.ev.logp_grad(qf, aux, out=(lp, gf))
         else:
-            l, g = self.ev.logp_grad(qf, self.aux)
+            l, g = self.ev.logp_grad(qf, aux)
             lp.copy_(l)
             gf.copy_(g)
         if self.rep is not None:
