@@ -96,8 +96,10 @@ banded_kernel(const __grid_constant__ EvalParams<T> p, int tiles_per_cta, int nt
   const int tid = threadIdx.x;
   const int c = blockIdx.x * blockDim.x + tid;  // < Cpad
   const int ch = blockIdx.y;
-  const int tile0 = ch * tiles_per_cta;
-  const int tile1 = min(tile0 + tiles_per_cta, ntiles_total);
+  // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile)
+  const int tile0 = tiles_per_cta > 0 ? ch * tiles_per_cta : (int)(((long long)ch * ntiles_total) / gridDim.y);
+  const int tile1 = tiles_per_cta > 0 ? min(tile0 + tiles_per_cta, ntiles_total)
+                                      : (int)(((long long)(ch + 1) * ntiles_total) / gridDim.y);
   const int my_tiles = tile1 - tile0;
 
   if (tid == 0) {
@@ -315,6 +317,14 @@ static bool use_x2(const lslb_plan* plan, int C) {
   return plan->desc.dtype == LSLB_F32 && C >= min_chains;
 }
 
+bool balanced_tiles() {
+  static const bool on = [] {
+    const char* e = getenv("LSLB_BALANCED_TILES");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+
 BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   BandedCfg k;
   const bool x2 = use_x2(plan, C);
@@ -354,7 +364,12 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   if (want < 1) want = 1;
   if (want > k.ntiles_total) want = k.ntiles_total;
   k.tiles_per_cta = (int)((k.ntiles_total + want - 1) / want);
-  k.nchunks = (k.ntiles_total + k.tiles_per_cta - 1) / k.tiles_per_cta;
+  if (balanced_tiles()) {
+    k.nchunks = (int)want;
+    k.tiles_per_cta = 0;  // the kernels partition the tiles evenly over the chunks
+  } else {
+    k.nchunks = (k.ntiles_total + k.tiles_per_cta - 1) / k.tiles_per_cta;
+  }
   return k;
 }
 

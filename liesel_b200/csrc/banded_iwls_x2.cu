@@ -39,8 +39,13 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);
   const int ch = blockIdx.y;
-  const int tile0 = ch * tiles_per_cta;
-  const int my_tiles = min(tile0 + tiles_per_cta, ntiles_total) - tile0;
+  // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile; with
+  // ceil(T / CTAs) tiles per CTA the last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others
+  // carried 56 tiles instead of 52.8)
+  // (tiles_per_cta > 0: the former ceil partition, kept for A/B runs: LSLB_BALANCED_TILES=0)
+  const int tile0 = tiles_per_cta > 0 ? ch * tiles_per_cta : (int)(((long long)ch * ntiles_total) / gridDim.y);
+  const int my_tiles = tiles_per_cta > 0 ? min(tile0 + tiles_per_cta, ntiles_total) - tile0
+                                         : (int)(((long long)(ch + 1) * ntiles_total) / gridDim.y) - tile0;
 
   auto tile_rows = [&](int t) -> int {
     long long rem = p.n - (long long)t * XR;
@@ -380,6 +385,8 @@ int launch_banded_iwls_x2(const lslb_plan* plan, const EvalParams<float>& ep, in
   return iwx2_target<FAM_NORMAL_FIXED, 2, 0>(tk, tm, tp, ep, p, nq, partial, k, st);
 }
 
+bool balanced_tiles();  // banded.cu
+
 BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C) {
   BandedCfg k;
   k.TC = 256;
@@ -392,7 +399,12 @@ BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C) {
   if (want > k.ntiles_total) want = k.ntiles_total;
   if (want < 1) want = 1;
   k.tiles_per_cta = (int)((k.ntiles_total + want - 1) / want);
-  k.nchunks = (k.ntiles_total + k.tiles_per_cta - 1) / k.tiles_per_cta;
+  if (balanced_tiles()) {
+    k.nchunks = (int)want;
+    k.tiles_per_cta = 0;  // the kernels partition the tiles evenly over the chunks
+  } else {
+    k.nchunks = (k.ntiles_total + k.tiles_per_cta - 1) / k.tiles_per_cta;
+  }
   return k;
 }
 

@@ -66,8 +66,13 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
   const int ch = blockIdx.y;
-  const int tile0 = ch * tiles_per_cta;
-  const int my_tiles = min(tile0 + tiles_per_cta, ntiles_total) - tile0;
+  // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile; with
+  // ceil(T / CTAs) tiles per CTA the last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others
+  // carried 56 tiles instead of 52.8)
+  // (tiles_per_cta > 0: the former ceil partition, kept for A/B runs: LSLB_BALANCED_TILES=0)
+  const int tile0 = tiles_per_cta > 0 ? ch * tiles_per_cta : (int)(((long long)ch * ntiles_total) / gridDim.y);
+  const int my_tiles = tiles_per_cta > 0 ? min(tile0 + tiles_per_cta, ntiles_total) - tile0
+                                         : (int)(((long long)(ch + 1) * ntiles_total) / gridDim.y) - tile0;
 #ifdef LSLB_X2_TRACE
   unsigned long long tr_t0 = x2_gtime();
   int tr_nonuni = 0;
