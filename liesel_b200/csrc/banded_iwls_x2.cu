@@ -33,7 +33,7 @@ struct IwRaw {
 template <int FAM, int NS, int PM, int TK, int TM, int TP, bool PAIRS, bool UNITY>
 __global__ void __launch_bounds__(128, 4)
 banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /*p of target*/,
-                      int nq, float* __restrict__ partial, int tiles_per_cta, int ntiles_total) {
+                      int nq, float* __restrict__ partial, int tiles_per_cta, int ntiles_total, int tiles_extra) {
   __shared__ __align__(128) IwRaw<NS, PAIRS> raw[XSTAGES];
   __shared__ __align__(8) u64 full[XSTAGES];
   const int tid = threadIdx.x;
@@ -42,10 +42,15 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
   // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile; with
   // ceil(T / CTAs) tiles per CTA the last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others
   // carried 56 tiles instead of 52.8)
-  // (tiles_per_cta > 0: the former ceil partition, kept for A/B runs: LSLB_BALANCED_TILES=0)
-  const int tile0 = tiles_per_cta > 0 ? ch * tiles_per_cta : (int)(((long long)ch * ntiles_total) / gridDim.y);
-  const int my_tiles = tiles_per_cta > 0 ? min(tile0 + tiles_per_cta, ntiles_total) - tile0
-                                         : (int)(((long long)(ch + 1) * ntiles_total) / gridDim.y) - tile0;
+  // tiles_per_cta = floor(T / chunks); the first `tiles_extra` chunks take one tile more. (Plain int
+  // arithmetic on purpose: the hot instantiation sits at 128 registers and a 64-bit division here made
+  // it spill - 5 % on H.)
+  // (written as ONE multiply of the block index by a selected constant: the hot instantiation sits at
+  //  128 registers and spilled - 5 % on H - with min(ch, extra) or a 64-bit division here)
+  const int tpa = ch < tiles_extra ? tiles_per_cta + 1 : tiles_per_cta;
+  const int tile0 = ch * tpa + (ch < tiles_extra ? 0 : tiles_extra);
+  const int my_tiles = tpa;
+  (void)ntiles_total;
 
   auto tile_rows = [&](int t) -> int {
     long long rem = p.n - (long long)t * XR;
@@ -334,7 +339,7 @@ static int iwx2_go(const EvalParams<float>& ep, int p, int nq, float* partial, c
   const bool unity = k.stages != 0;  // banded_iwls_cfg: plan->unit_rows
 #define LSLB_IW_GO(PR, UN)                                                                         \
   banded_iwls_x2_kernel<FAM, NS, PM, TK, TM, TP, PR, UN><<<grid, block, 0, st>>>(ep, p, nq, partial, \
-                                                                                 k.tiles_per_cta, k.ntiles_total)
+                                                                                 k.tiles_per_cta, k.ntiles_total, k.tiles_extra)
   if constexpr (TK == 0) {
     if (pairs) { if (unity) LSLB_IW_GO(true, true); else LSLB_IW_GO(true, false); }
     else { if (unity) LSLB_IW_GO(false, true); else LSLB_IW_GO(false, false); }
@@ -385,8 +390,6 @@ int launch_banded_iwls_x2(const lslb_plan* plan, const EvalParams<float>& ep, in
   return iwx2_target<FAM_NORMAL_FIXED, 2, 0>(tk, tm, tp, ep, p, nq, partial, k, st);
 }
 
-bool balanced_tiles();  // banded.cu
-
 BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C) {
   BandedCfg k;
   k.TC = 256;
@@ -399,12 +402,12 @@ BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C) {
   if (want > k.ntiles_total) want = k.ntiles_total;
   if (want < 1) want = 1;
   k.tiles_per_cta = (int)((k.ntiles_total + want - 1) / want);
-  if (balanced_tiles()) {
-    k.nchunks = (int)want;
-    k.tiles_per_cta = 0;  // the kernels partition the tiles evenly over the chunks
-  } else {
-    k.nchunks = (k.ntiles_total + k.tiles_per_cta - 1) / k.tiles_per_cta;
-  }
+  // balanced partition: chunk sizes differ by at most one tile (with ceil(T / CTAs) tiles per CTA the
+  // last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others carried 56 tiles instead of 52.8:
+  // 2-4 % at 64..512 chains, A/B on one box)
+  k.nchunks = (int)want;
+  k.tiles_per_cta = k.ntiles_total / k.nchunks;
+  k.tiles_extra = k.ntiles_total % k.nchunks;
   return k;
 }
 

@@ -57,7 +57,7 @@ template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S>
 #define LSLB_X2_STAGES 6  // ring depth: how many tiles the fastest warp of a CTA may run ahead of the slowest
 #endif
 __global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA (or 2 x 8, 4 x 4 for few chains)
-banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total) {
+banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total, int tiles_extra) {
   __shared__ __align__(128) XRaw<NS> raw[X2S];
   __shared__ __align__(8) u64 full[X2S];
   __shared__ int done[X2S];  // warps that have finished with the tile in stage s
@@ -69,10 +69,15 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile; with
   // ceil(T / CTAs) tiles per CTA the last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others
   // carried 56 tiles instead of 52.8)
-  // (tiles_per_cta > 0: the former ceil partition, kept for A/B runs: LSLB_BALANCED_TILES=0)
-  const int tile0 = tiles_per_cta > 0 ? ch * tiles_per_cta : (int)(((long long)ch * ntiles_total) / gridDim.y);
-  const int my_tiles = tiles_per_cta > 0 ? min(tile0 + tiles_per_cta, ntiles_total) - tile0
-                                         : (int)(((long long)(ch + 1) * ntiles_total) / gridDim.y) - tile0;
+  // tiles_per_cta = floor(T / chunks); the first `tiles_extra` chunks take one tile more. (Plain int
+  // arithmetic on purpose: the hot instantiation sits at 128 registers and a 64-bit division here made
+  // it spill - 5 % on H.)
+  // (written as ONE multiply of the block index by a selected constant: the hot instantiation sits at
+  //  128 registers and spilled - 5 % on H - with min(ch, extra) or a 64-bit division here)
+  const int tpa = ch < tiles_extra ? tiles_per_cta + 1 : tiles_per_cta;
+  const int tile0 = ch * tpa + (ch < tiles_extra ? 0 : tiles_extra);
+  const int my_tiles = tpa;
+  (void)ntiles_total;
 #ifdef LSLB_X2_TRACE
   unsigned long long tr_t0 = x2_gtime();
   int tr_nonuni = 0;
@@ -530,11 +535,11 @@ static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cu
 #define LSLB_X2_GO(ST)                                                                                           \
   do {                                                                                                           \
     if (unity) {                                                                                                 \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);   \
-      else banded_x2_kernel<FAM, NS, PM, false, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);    \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);   \
+      else banded_x2_kernel<FAM, NS, PM, false, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);    \
     } else {                                                                                                     \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);  \
-      else banded_x2_kernel<FAM, NS, PM, false, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total);   \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);  \
+      else banded_x2_kernel<FAM, NS, PM, false, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);   \
     }                                                                                                            \
   } while (0)
   if (k.stages >= LSLB_X2_STAGES) LSLB_X2_GO(LSLB_X2_STAGES);

@@ -266,6 +266,7 @@ LaunchCfg choose_cfg(const lslb_plan* plan, int C, size_t smem_per_chain, size_t
 struct BandedCfg {
   int TC, Cpad, ntiles_chain, ntiles_total, tiles_per_cta, nchunks;
   int tc_eff = 0;  // banded_x2: chains a CTA really owns (multiple of 64, <= TC); 0 = TC
+  int tiles_extra = 0;  // the first tiles_extra row chunks take tiles_per_cta + 1 tiles (balanced partition)
   int stages = 6;  // banded_x2: depth of the TMA ring (6; 3 / 2 for the 2- / 1-warp CTAs of small chain counts)
 };
 struct TcCfg {

@@ -226,6 +226,9 @@ class AsyncNUTS:
                 if nd >= self.C:
                     break
                 self._maybe_compact(nd)
+                # a chain needs at most 2^max_treedepth evaluations (+ the refresh) per transition
+                if self.steps - n0 > (target if stage == "posterior" else self.W) * (2 ** self.maxd + 2) + check_every:
+                    raise RuntimeError("asynchronous NUTS: a chain did not finish its stage (state machine stuck)")
             sync()
             out["steps_" + stage] = self.steps - n0
             out["seconds_" + stage] = time.perf_counter() - t0

@@ -201,3 +201,18 @@ def test_liesel_named_state_serves_an_unmodified_tau2_gibbs_kernel():
     params, aux = iface.pack(state2)
     assert params.shape == (1, 42) and aux.shape == (1, 2)
     assert float(aux[0, 0]) == float(pos[position_key])
+
+
+def test_headline_kernel_instantiation_does_not_spill():
+    """The H instantiation of ``banded_x2_kernel`` sits exactly at 128 registers (16 warps per SM):
+    an innocent-looking change of its prologue made ptxas spill 150 bytes and cost 5 % on the headline
+    (round 2: a 64-bit division in the tile partition). The build log is the early warning."""
+    log = os.path.join(ROOT, "liesel_b200", "csrc", "build", "banded_x2.log")
+    if not os.path.exists(log):
+        pytest.skip("no build log (the library was not built in this tree)")
+    text = open(log).read()
+    key = "banded_x2_kernelILi0ELi2ELi2ELb1ELb1ELi6E"  # <FAM_NORMAL_LS, NS=2, PM=2, GRAD, UNITY, 6 stages>
+    i = text.index("Function properties for _ZN4lslb16" + key)
+    block = text[i: i + 400]
+    assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in block, block
+    assert "Used 128 registers" in block or "Used 12" in block
