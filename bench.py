@@ -689,9 +689,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(C_ * (P + A) * 4), "d2h_bytes_per_step": int(C_ * (P + 1) * 4),
                 "api": "B200Interface.log_prob_and_grad on pinned host buffers"},
-        # per step: gather_small_kernel, the row-streaming kernel, finalize_rows_kernel, finalize_logp_kernel
-        # (ncu launch list: profiles/r02_launches.md)
-        "gpu_launches": int(4 * K),
+        # per step: gather_small_kernel, the row-streaming kernel, finalize_rows_kernel (the log-posterior is
+        # added by its last CTA per chain group) - ncu launch list: profiles/r02_launches.md
+        "gpu_launches": int(3 * K),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "ess": ess,

@@ -285,7 +285,7 @@ template <typename T, int FIN_G>
 __device__ __forceinline__ void finalize_grad_body(const FinalizeParams& fp, const T* __restrict__ partial,
                                                    const T* __restrict__ pT, const T* __restrict__ aux,
                                                    T* __restrict__ grad, T* __restrict__ vsum,
-                                                   double* __restrict__ qf) {
+                                                   double* qf) {
   // One CTA per (32 chains, coefficient row j). It reduces the row's chunk partials (gradient of the
   // likelihood), adds the prior's gradient and ALSO emits the row's share of the prior's quadratic
   // form, qf[j][c] = -1/2 x_j (K x)_j / tau2 (or -1/2 (x_j - m)^2 / s^2): the log-posterior kernel
@@ -370,18 +370,20 @@ template <typename T, int FIN_G>
 __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, const T* __restrict__ partial,
                                                    const T* __restrict__ pT, const T* __restrict__ aux,
                                                    const T* __restrict__ gpl, int gtiles, int G,
-                                                   const double* __restrict__ qf, T* __restrict__ logp) {
+                                                   const double* qf, T* __restrict__ logp) {
+  // runs in the LAST CTA of a chain group inside finalize_rows_kernel: qf was written by other CTAs of
+  // the same launch, so it is read with ld.global.cg (L2), never through the non-coherent path
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;  // < Cpad (Cpad is a multiple of 32)
   const int g = threadIdx.y;
   const bool with_prior = !(fp.flags & LSLB_SKIP_PRIOR);
   (void)G;
   // log-likelihood: summed over the row chunks by the extra slice of finalize_rows_kernel (row Psmall of qf)
-  double acc = g == 0 ? qf[(size_t)fp.Psmall * fp.Cpad + c] : 0.0;
+  double acc = g == 0 ? __ldcg(qf + (size_t)fp.Psmall * fp.Cpad + c) : 0.0;
   // quadratic forms of the priors: one number per coefficient row from finalize_grad_body, plus the
   // group block's per-tile partials
   if (with_prior) {
-    for (int j = g; j < fp.Preal; j += FIN_G) acc += qf[(size_t)j * fp.Cpad + c];
+    for (int j = g; j < fp.Preal; j += FIN_G) acc += __ldcg(qf + (size_t)j * fp.Cpad + c);
     for (int b = 0; b < fp.nblocks; ++b) {
       const PriorP& pr = fp.pr[b];
       if (pr.prior == LSLB_PRIOR_NORMAL && pr.soff < 0) {  // group block: reduced per 32-group tile
@@ -422,7 +424,7 @@ __device__ __forceinline__ void finalize_logp_body(const FinalizeParams& fp, con
 // the row chunks (Kahan pairs hi - lo) in double, into row Psmall of qf.
 template <typename T, int FIN_G>
 __device__ __forceinline__ void finalize_loglik_body(const FinalizeParams& fp, const T* __restrict__ partial,
-                                                     double* __restrict__ qf) {
+                                                     double* qf) {
   __shared__ double red[FIN_G][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int g = threadIdx.y;
@@ -451,23 +453,29 @@ __device__ __forceinline__ void finalize_loglik_body(const FinalizeParams& fp, c
   qf[(size_t)fp.Psmall * fp.Cpad + c] = acc;
 }
 
-// Two launches per call: finalize_rows_kernel (grid.y = Psmall: gradient rows + the rows' shares of the
-// priors' quadratic forms; value-only calls run it with grad == NULL) and finalize_logp_kernel (one CTA
-// per 32 chains: log-likelihood chunks + Psmall numbers + constants).
-template <typename T, int FIN_G>
-__global__ void __launch_bounds__(32 * FIN_G)
-finalize_logp_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
-                     const T* __restrict__ pT, const T* __restrict__ aux, const T* __restrict__ gpl,
-                     int gtiles, int G, const double* __restrict__ qf, T* __restrict__ logp) {
-  finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, qf, logp);
-}
+// ONE launch per call. grid.y = Psmall + 1 slices per 32 chains: gradient rows + the rows' shares of the
+// priors' quadratic forms (value-only calls: grad == NULL) and the log-likelihood slice. The LAST slice
+// of a chain group to finish (a counter per chain group, zeroed by gather_small_kernel earlier in the
+// same call; __threadfence before the increment, coherent loads after it) adds the Psmall + 1 numbers
+// and the constants into the log-posterior. The sum is over fixed rows in a fixed order: which CTA
+// happens to be last does not change a bit of the result.
 template <typename T, int FIN_G>
 __global__ void __launch_bounds__(32 * FIN_G)
 finalize_rows_kernel(const __grid_constant__ FinalizeParams fp, const T* __restrict__ partial,
                      const T* __restrict__ pT, const T* __restrict__ aux, T* __restrict__ grad,
-                     T* __restrict__ vsum, double* __restrict__ qf) {
+                     T* __restrict__ vsum, double* qf, const T* __restrict__ gpl, int gtiles, int G,
+                     int* __restrict__ counters, T* __restrict__ logp) {
+  __shared__ int is_last;
   if ((int)blockIdx.y < fp.Psmall) finalize_grad_body<T, FIN_G>(fp, partial, pT, aux, grad, vsum, qf);
   else finalize_loglik_body<T, FIN_G>(fp, partial, qf);
+  __threadfence();  // this CTA's qf row is visible device-wide before the counter moves
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0)
+    is_last = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  finalize_logp_body<T, FIN_G>(fp, partial, pT, aux, gpl, gtiles, G, qf, logp);
 }
 
 // =======================================================================================
@@ -541,6 +549,7 @@ static LaunchCfg eval_cfg(const lslb_plan* plan, int C) {
 template <typename T>
 struct WsLayout {
   T *pT, *partial, *bT, *gbT, *gpl, *rt, *vsum;
+  int* counters;  // [Cpad / 32] finished slices per chain group (last-CTA-done reduction of the log-posterior)
   double* qf;  // [(Psmall + 1) x Cpad] per-row shares of the priors' quadratic forms; last row: log-likelihood
   int gtiles;
   size_t bytes;
@@ -560,6 +569,8 @@ static WsLayout<T> layout_ws(const lslb_plan* plan, const LaunchCfg& k, void* ws
   L.vsum = take((size_t)2 * k.Cpad);  // residual sums of the (at most two) centring rows
   L.qf = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
   off += align_up((size_t)(plan->Psmall + 1) * k.Cpad * sizeof(double), 256);
+  L.counters = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + off);  // one per 32 chains
+  off += align_up((size_t)(k.Cpad / 32) * sizeof(int), 256);
   L.gtiles = 0;
   L.bT = L.gbT = L.gpl = nullptr;
   if (plan->grp >= 0) {
@@ -732,7 +743,7 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   ep.bT = L.bT;
   ep.gbT = L.gbT;
 
-  if (int gst = launch_gather_small<T>(fp, params, L.pT, stream)) return gst;
+  if (int gst = launch_gather_small<T>(fp, params, L.pT, stream, L.counters, k.Cpad / 32)) return gst;
   int G = 0;
   if (plan->grp >= 0) {
     const lslb_block_desc& d = plan->blk[plan->grp];
@@ -777,12 +788,11 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
     dim3 fgrid(k.Cpad / 32, plan->Psmall + 1);  // last slice: the log-likelihood
     T* gout = g ? grad : nullptr;
     if ((long long)fgrid.x * fgrid.y >= 4LL * plan->sm_count)
-      finalize_rows_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf);
+      finalize_rows_kernel<T, 8><<<fgrid, dim3(32, 8), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf,
+                                                                    L.gpl, L.gtiles, G, L.counters, logp);
     else
-      finalize_rows_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf);
-    LSLB_LAUNCH_CHECK();
-    finalize_logp_kernel<T, 32><<<k.Cpad / 32, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux,
-                                                                          L.gpl, L.gtiles, G, L.qf, logp);
+      finalize_rows_kernel<T, 32><<<fgrid, dim3(32, 32), 0, stream>>>(fp, L.partial, L.pT, aux, gout, L.vsum, L.qf,
+                                                                      L.gpl, L.gtiles, G, L.counters, logp);
     LSLB_LAUNCH_CHECK();
   }
   if (g) {

@@ -18,6 +18,13 @@
 // with two barriers per block. One CTA per SM and chain tile; at the end the row slices of a smooth
 // are summed in slice order through shared memory, so results are bitwise reproducible. Shared-memory
 // traffic per row, smooth and 64 chains: one 512-byte store + two 512-byte loads instead of twelve.
+//
+// Measured (round 2, profiles/r02_s2_msmooth_full.md): 90 us for S2 (the generic kernel: 110), the call
+// 0.124 ms. 384 warp instructions per row of which 40 are packed FMAs: every row and smooth pays a
+// constant-table load + indirect branch + reconvergence, and 15 warps per SM cannot hide the dependent
+// latencies (issue slots 42 % busy, FMA pipe 20 %; stalls: wait 3.0, barrier 1.4, branch resolving 1.1
+// per issued instruction). Grouping four rows per dispatch to batch the shared-memory loads was slower
+// (101 us: spills at the 128-register cap); so was the chunk-sorted layout of msort_x2.cu (122 us).
 #include "common.cuh"
 #include "x2_common.cuh"
 

@@ -14,7 +14,11 @@ namespace lslb {
 // ncoef x nblocks dependent double FMAs on strided loads (12 us at the S2 size).
 template <typename T>
 __global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
-                                    const T* __restrict__ params, T* __restrict__ pT, int nb_real) {
+                                    const T* __restrict__ params, T* __restrict__ pT, int nb_real,
+                                    int* __restrict__ zero_ints, int nz) {
+  // (also clears the per-chain-group counters of this call's finalize kernel: same stream, earlier launch)
+  if (zero_ints != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) zero_ints[i] = 0;
   if ((int)blockIdx.x >= nb_real) {
     const int wpb = blockDim.x >> 5;
     const int per_v = (fp.Cpad + wpb - 1) / wpb;  // blocks per virtual row
@@ -57,13 +61,14 @@ __global__ void gather_small_kernel(const __grid_constant__ FinalizeParams fp,
 }
 
 template <typename T>
-inline int launch_gather_small(const FinalizeParams& fp, const T* params, T* pT, cudaStream_t stream) {
+inline int launch_gather_small(const FinalizeParams& fp, const T* params, T* pT, cudaStream_t stream,
+                               int* zero_ints = nullptr, int nz = 0) {
   const long long total = (long long)fp.Preal * fp.Cpad;
   const int nb_real = (int)((total + 255) / 256);
   const int nv = fp.Psmall - fp.Preal;
   const int nb = nb_real + nv * ((fp.Cpad + 7) / 8);
-  if (nb > 0) {
-    gather_small_kernel<T><<<(unsigned)nb, 256, 0, stream>>>(fp, params, pT, nb_real);
+  if (nb > 0 || zero_ints != nullptr) {
+    gather_small_kernel<T><<<(unsigned)(nb > 0 ? nb : 1), 256, 0, stream>>>(fp, params, pT, nb_real, zero_ints, nz);
     LSLB_LAUNCH_CHECK();
   }
   return LSLB_OK;
