@@ -223,7 +223,7 @@ def measure_pipe_peaks(torch, _lib, sm_count):
         def go():
             _lib.check(_lib.bench_lib().lslb_debug_pipe_peak(kind, sm_count * 8, iters, _lib.ptr(sink),
                                                              C.byref(work), _lib.stream_ptr()), "pipe_peak")
-        for rep in range(4):
+        for rep in range(10):  # best of nine after one discarded repetition
             # the timed launch is queued BEHIND an untimed one, so the start event is stamped when the
             # stream is busy and the timed kernel follows it without a host-side gap (under torchrun the
             # ranks' host threads compete and a late launch used to be counted as kernel time)
