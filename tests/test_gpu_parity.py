@@ -881,6 +881,26 @@ def test_full_size_s2_against_oracle(lb):
     check_iwls(spec, plan, "loc_np3", th, aux, chains=[0, 63])
 
 
+def test_chunk_sorted_multi_smooth_experiment_matches_oracle(lb, monkeypatch):
+    """``msort_x2_kernel`` (opt-in, ``LSLB_MSORT=1`` at plan creation; slower than ``msmooth_x2`` and
+    therefore not the default) must still be CORRECT: S2 with its centred smooths, value + gradient
+    against the fp64 oracle, and the same numbers as the default kernel to float rounding."""
+    spec, centre = make("s2", np.float32)
+    th, aux = synth.evaluation_points(spec, centre, 64, tau2="loguniform")
+    plan_default = lb.Plan(spec)
+    assert plan_default.variant == "multi_smooth_x2"
+    lp0, g0 = plan_default.logp_grad(dev(th, plan_default), dev(aux, plan_default))
+    monkeypatch.setenv("LSLB_MSORT", "1")
+    plan = lb.Plan(spec)
+    monkeypatch.delenv("LSLB_MSORT")
+    assert plan.variant == "multi_smooth_chunk_sorted_x2"
+    check_logp_grad(spec, plan, th, aux, chains=[0, 31, 63])
+    lp1, g1 = plan.logp_grad(dev(th, plan), dev(aux, plan))
+    torch.testing.assert_close(lp1, lp0, rtol=2e-6, atol=0)
+    scale = g0.abs().amax(dim=0, keepdim=True).clamp_min(1.0)
+    assert float(((g1 - g0).abs() / scale).max()) < 2e-5
+
+
 # --- Metropolis-Hastings step (goose/mh.py) ------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_mh_step_decisions_match_the_reference_rule(dtype):

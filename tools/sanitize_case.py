@@ -49,3 +49,30 @@ if which in ("all", "group"):
 if which in ("all", "tc"):
     spec, centre = synth.s4_logistic(n=33_000, p=128)
     run("s4 tensor cores C=256", spec, centre, 256)
+if which in ("all", "round2"):
+    # round-2 kernels: small-chain ring depths (1- and 2-warp CTAs), multi-smooth kernels (msmooth / msort),
+    # finalize with the last-CTA-done log-posterior, IWLS with weight products + parallel chunk reduce,
+    # warp-cooperative centring rows, the asynchronous NUTS state machine with Gibbs blocks
+    spec, centre = synth.s3_gamlss(n=9_000 + 13)
+    run("s3 C=64 (1-warp CTAs, 2 stages)", spec, centre, 64, iwls_block="scale_np0")
+    run("s3 C=128 (2-warp CTAs, 3 stages)", spec, centre, 128, iwls_block="loc_p0")
+    spec, centre = synth.s2_pspline_gam(n=6_000 + 5)
+    run("s2 msmooth C=64", spec, centre, 64, iwls_block="loc_np3")
+    run("s2 msmooth C=96", spec, centre, 96)
+    os.environ["LSLB_MSORT"] = "1"
+    run("s2 msort C=64", spec, centre, 64)
+    os.environ.pop("LSLB_MSORT")
+    from liesel_b200 import reparam
+    from liesel_b200.nuts_gibbs import AsyncNutsGibbs, PlanEvaluator
+
+    spec, centre = synth.s3_gamlss(n=3_000)
+    plan = Plan(spec)
+    cm = {b.name: plan.column_means(b.name) for b in spec.blocks if b.kind == 1}
+    rep = reparam.sum_to_zero(spec, cm, device=plan.device)
+    th, aux = synth.evaluation_points(spec, centre, 40, seed=1)
+    run_a = AsyncNutsGibbs(spec, PlanEvaluator(plan), torch.as_tensor(th, device="cuda"),
+                           torch.as_tensor(aux, device="cuda"), 40, 6, reparam=rep, seed=1, max_treedepth=4,
+                           epoch_kw=dict(init_duration=10, term_duration=10, base_duration=10))
+    t = run_a.run(check_every=16)
+    assert torch.isfinite(run_a.draws()).all()
+    print("async nuts-gibbs ok", t["steps_warmup"], t["steps_posterior"], flush=True)
