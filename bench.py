@@ -281,6 +281,32 @@ def _flops(name, n, C, p=0):
     return float(n) * C * per_row
 
 
+def s3_iwls_sampler(torch, spec, plan, params, aux, warmup=200, samples=300):
+    """BASELINE config 3 as a SAMPLER: an IWLS kernel per coefficient block + Gibbs tau2 (what
+    ``dist_reg_mcmc`` configures, model/distreg.py:300-349), spline blocks in the sum-to-zero coordinates."""
+    from liesel_b200 import diagnostics, reparam
+    from liesel_b200.iwls_sampler import IWLSGibbsSampler
+
+    cons = {b.name: reparam.sum_to_zero_basis(plan.column_means(b.name)) for b in spec.blocks if b.kind == 1}
+    smp = IWLSGibbsSampler(plan, params, aux, seed=1, constraints=cons)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    smp.warmup(warmup)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    draws, _, infos = smp.sample(samples)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    ess = diagnostics.ess_bulk_device(draws)
+    acc = [float(np.mean([float(i[b.name]["acceptance_prob"].mean()) for i in infos])) for b in smp.blocks]
+    return {"chains": int(draws.shape[1]), "warmup_iters": warmup, "posterior_iters": samples,
+            "iterations_per_s": samples / (t2 - t1), "posterior_seconds": t2 - t1, "warmup_seconds": t1 - t0,
+            "ess_bulk_min": float(ess.min()), "split_rhat_max": float(np.max(diagnostics.split_rhat_device(draws))),
+            "ess_per_sec_posterior": float(ess.min() / (t2 - t1)), "mean_accept_min_over_blocks": min(acc),
+            "evals": dict(smp.evals),
+            "what": "IWLS transition per block (2 score+information+Cholesky passes + 1 log-posterior) + Gibbs tau2"}
+
+
 def secondary_single_gpu(torch, dist, dev, flush, fp32_peak, tf32x3_note, reps=10):
     """S2, S3 (+ one IWLS pass), one S4 shard and S5 at BASELINE.json's sizes on one GPU."""
     from liesel_b200 import synth
@@ -320,6 +346,7 @@ def secondary_single_gpu(torch, dist, dev, flush, fp32_peak, tf32x3_note, reps=1
             if name == "S3":
                 fi = _flops("S3_iwls", spec.n, C)
                 ent["iwls"]["frac_of_fp32_peak"] = fi / (ms_i * 1e-3) / 1e12 / fp32_peak
+                ent["iwls_sampler"] = s3_iwls_sampler(torch, spec, plan, t, a)
         out.append(ent)
         del plan, t, a
         torch.cuda.empty_cache()

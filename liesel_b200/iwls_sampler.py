@@ -27,16 +27,28 @@ import math
 
 import torch
 
-from .plan import Plan, iwls_propose, mh_step
+from .plan import Plan, chol as chol_info, iwls_propose, mh_step
 
 
 class IWLSGibbsSampler:
     def __init__(self, plan: Plan, params: torch.Tensor, aux: torch.Tensor | None, seed: int = 0,
                  blocks: list[str] | None = None, initial_step_size: float = 0.01,
                  da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
-                 da_t0: int = 10, gibbs: bool = True):
+                 da_t0: int = 10, gibbs: bool = True, constraints: dict | None = None):
+        """``constraints``: block name -> ``Z [k, k_r]`` with orthonormal columns (e.g.
+        ``reparam.sum_to_zero_basis`` of the basis' column means): the block is sampled in the
+        coordinates ``gamma`` of ``beta = Z gamma`` — the constrained design ``B Z`` with penalty
+        ``Z' K Z`` that a Liesel user passes to ``add_np_smooth`` for identifiability next to an
+        intercept. Score and information transform as ``Z' s`` and ``Z' I Z``; the start values are
+        projected onto the constrained space."""
         self.plan, self.spec = plan, plan.spec
         self.params = params.clone().contiguous()
+        self.Z = {k: torch.as_tensor(v, dtype=params.dtype, device=params.device).contiguous()
+                  for k, v in (constraints or {}).items()}
+        for name, Z in self.Z.items():
+            b = self.spec.block(name)
+            sl = slice(b.param_offset, b.param_offset + b.ncoef)
+            self.params[:, sl] = (self.params[:, sl] @ Z) @ Z.t()
         self.aux = None if aux is None else aux.clone().contiguous()
         self.C = params.shape[0]
         self.dev, self.dt = params.device, params.dtype
@@ -78,17 +90,29 @@ class IWLSGibbsSampler:
         chol = torch.where(bad[:, None, None], eye, chol)
         return chol.contiguous(), bad.to(torch.int32) * 2
 
+    def _score_chol(self, blk, params):
+        """Score and Cholesky factor of the (ridged) information in the SAMPLED coordinates."""
+        Z = self.Z.get(blk.name)
+        if Z is None:
+            score, _, ch = self.plan.iwls(blk.name, params, self.aux)
+            return score, ch
+        score, info, _ = self.plan.iwls(blk.name, params, self.aux, want_chol=False)
+        info_r = torch.matmul(Z.t(), torch.matmul(info, Z)).contiguous()
+        return (score @ Z).contiguous(), chol_info(info_r)
+
     def iwls_transition(self, blk, adapt_t: int | None = None):
         sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
         step = self.step[blk.name]
-        pos = self.params[:, sl].contiguous()
-        score, _, chol = self.plan.iwls(blk.name, self.params, self.aux)
+        Z = self.Z.get(blk.name)
+        beta = self.params[:, sl]
+        pos = (beta if Z is None else beta @ Z).contiguous()
+        score, chol = self._score_chol(blk, self.params)
         chol, code = self._safe_chol(chol)
         z = torch.randn(pos.shape, generator=self.gen, device=self.dev, dtype=self.dt)
         prop, fwd = iwls_propose(pos, score, chol, step, z=z)
         params_prop = self.params.clone()
-        params_prop[:, sl] = prop
-        score_p, _, chol_p = self.plan.iwls(blk.name, params_prop, self.aux)
+        params_prop[:, sl] = prop if Z is None else prop @ Z.t()
+        score_p, chol_p = self._score_chol(blk, params_prop)
         chol_p, _ = self._safe_chol(chol_p)
         _, bwd = iwls_propose(prop, score_p, chol_p, step, x_eval=pos)
         lp_prop, _ = self.plan.logp_grad(params_prop, self.aux, want_grad=False)

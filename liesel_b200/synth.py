@@ -40,10 +40,14 @@ def s1_blr(n: int = 1000, p: int = 10, dtype=np.float32, seed: int = 101):
 
 
 def s2_pspline_gam(n: int = 100_000, n_smooth: int = 5, k: int = 20, dtype=np.float32,
-                   seed: int = 102):
+                   seed: int = 102, center: bool = True, intercept: bool = False):
     """
     S2: additive model with n_smooth cubic P-splines, sigma fixed at 0.5, tau2 ~ IG(1, 0.005).
-    Each basis is column-centred (B - 1 cbar^T) so that the smooths do not absorb a level.
+    ``center=True`` (the evaluation benchmark's form): each basis is column-centred (B - 1 cbar^T,
+    SURVEY 8d). Note that column-centring alone leaves the constant coefficient vector in the null space
+    of BOTH the design and the difference penalty, so that form is for timing evaluations, not for
+    sampling. ``center=False, intercept=True``: plain bases next to an intercept — the model to SAMPLE,
+    under the sum-to-zero constraint of ``reparam.sum_to_zero`` (the constrained design ``B Z``).
     """
     rng = np.random.default_rng(seed)
     xs = rng.uniform(size=(n_smooth, n))
@@ -54,12 +58,16 @@ def s2_pspline_gam(n: int = 100_000, n_smooth: int = 5, k: int = 20, dtype=np.fl
     spec.fixed_scale = 0.5
     K = pspline_penalty(k, 2)
     centre = []
+    if intercept:
+        spec.add_p_smooth(np.ones((n, 1)), 0.0, 100.0, "loc", "loc_p0")
+        centre.append(np.array([float(np.mean(f))]))
     for j in range(n_smooth):
         xj = xs[j].astype(dtype)
         knots = equidistant_knots(xj, k, 3)
         spec.add_spline_smooth(xj, knots, K, 1.0, 0.005, "loc", f"loc_np{j}", tau2_init=1.0,
-                               center=True)
-        centre.append(np.sin(2 * np.pi * _greville(knots.astype(np.float64)) * (j + 1) / 2))
+                               center=center)
+        cj = np.sin(2 * np.pi * _greville(knots.astype(np.float64)) * (j + 1) / 2)
+        centre.append(cj - cj.mean() if intercept else cj)
     return spec, np.concatenate(centre)
 
 
