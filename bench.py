@@ -486,6 +486,13 @@ def run_ess(args, torch, dev, plan, spec, centre, local):
         "warmup_iters": W, "warmup_term_duration": args.ess_term, "posterior_iters": S,
         "clocks": clocks,
     })
+    # ---- for comparison on the same model and chain count: the IWLS-within-Gibbs scheme (what Liesel's
+    #      dist_reg_mcmc configures by default, model/distreg.py:300-349) - not the NUTS metric, reported beside it
+    try:
+        out["iwls_sampler_same_model"] = s3_iwls_sampler(torch, spec, plan, torch.as_tensor(th0, device=dev),
+                                                         torch.as_tensor(aux0, device=dev))
+    except Exception as e:  # never let the side entry take the metric down
+        out["iwls_sampler_same_model"] = {"error": repr(e)[:200]}
     # ---- CPU arm: the same sampler on the oracle's CPU port, host cores ----------------------
     cpu = None
     if not args.no_cpu_baseline:
