@@ -49,7 +49,10 @@ __device__ __forceinline__ unsigned x2_smid() {
 // X2S: depth of the TMA ring (tiles the fastest warp may run ahead of the slowest). 6 for the 4..16-warp
 // CTAs; the 2- and 1-warp CTAs of small chain counts take 3 and 2 stages so that 8 / 16 of them fit an
 // SM's shared memory (with 6 stages = 34 KB each only 6 did: 6 resident warps at 64 chains).
-template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S>
+// SHW: both smooths are splines of the SAME covariate on the same knots (H / S3: mean and log-sd smooths of
+// one x; checked bit for bit at plan creation): one copy of the weights and spans is staged and held in
+// registers for both (32 registers and half of the shared-memory loads of the hot loop).
+template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S, int NSL = NS>  // NSL: bands loaded (1 = shared)
 #ifndef LSLB_X2_NRB
 #define LSLB_X2_NRB 4   // rows per register block (4 or 2)
 #endif
@@ -58,10 +61,11 @@ template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S>
 #endif
 __global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA (or 2 x 8, 4 x 4 for few chains)
 banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total, int tiles_extra) {
-  __shared__ __align__(128) XRaw<NS> raw[X2S];
+  constexpr bool SHW = NSL < NS;
+  __shared__ __align__(128) XRaw<NSL> raw[X2S];
   __shared__ __align__(8) u64 full[X2S];
   __shared__ int done[X2S];  // warps that have finished with the tile in stage s
-  __shared__ __align__(16) float tws[X2S][NS][4];  // the tile's weight-column sums (plan constant)
+  __shared__ __align__(16) float tws[X2S][NSL][4];  // the tile's weight-column sums (plan constant)
 
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
@@ -106,13 +110,13 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   };
   auto issue = [&](int t, int s) {
     const long long r0 = (long long)t * XR;
-    constexpr unsigned bytes = XR * 4 + NS * (XR * 16 + XR * 4 + 16);
+    constexpr unsigned bytes = XR * 4 + NSL * (XR * 16 + XR * 4 + 16);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(&full[s])),
                  "r"(bytes)
                  : "memory");
     bulk(raw[s].y, p.y + r0, XR * 4, &full[s]);
 #pragma unroll
-    for (int m = 0; m < NS; ++m) {
+    for (int m = 0; m < NSL; ++m) {
       bulk(raw[s].w[m], p.sp[m].w + 4 * r0, XR * 16, &full[s]);
       bulk(raw[s].start[m], p.sp[m].start + r0, XR * 4, &full[s]);
       bulk(tws[s][m], p.sp[m].tw + 4 * (long long)t, 16, &full[s]);
@@ -226,7 +230,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     const int t = tile0 + k;
     const int s = k % X2S;
     const int rows = tile_rows(t);
-    XRaw<NS>& D = raw[s];
+    XRaw<NSL>& D = raw[s];
     if (rows == XR) {
       wait_full(s, (k / X2S) & 1);
     } else {  // ragged last tile of the data: ordinary loads (bulk copies need 16-byte multiples)
@@ -235,7 +239,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       for (int r = tid; r < rows; r += blockDim.x) {
         D.y[r] = p.y[r0 + r];
 #pragma unroll
-        for (int m = 0; m < NS; ++m) {
+        for (int m = 0; m < NSL; ++m) {
           D.start[m][r] = p.sp[m].start[r0 + r];
 #pragma unroll
           for (int u = 0; u < 4; ++u) D.w[m][4 * r + u] = p.sp[m].w[4 * (r0 + r) + u];
@@ -247,7 +251,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     // is every smooth's span constant over this tile? (each warp evaluates it redundantly)
     bool uni = true;
 #pragma unroll
-    for (int m = 0; m < NS; ++m) {
+    for (int m = 0; m < NSL; ++m) {
       const int first = D.start[m][0];
       bool eq = true;
       for (int r = (tid & 31); r < rows; r += 32) eq = eq && (D.start[m][r] == first);
@@ -260,7 +264,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
     // NR rows whose weights/responses are already in registers: forward with wb fixed across rows
     // (u-major), likelihood, backward with the residual fixed across the four weights of a row
-    auto compute_block = [&](const float (&w)[NS][4][4], const float (&yv)[4], auto NRtag, auto FASTtag) {
+    auto compute_block = [&](const float (&w)[NSL][4][4], const float (&yv)[4], auto NRtag, auto FASTtag) {
       constexpr int NR = decltype(NRtag)::value;
       constexpr bool FAST = decltype(FASTtag)::value;
       u64 eta0[NR], eta1[NR];
@@ -273,8 +277,8 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           if (FAST && u == 1) continue;
 #pragma unroll
           for (int i = 0; i < NR; ++i) {
-            if ((PM >> m) & 1) eta1[i] = fma2(bc(w[m][i][u]), wb[m][u], eta1[i]);
-            else eta0[i] = fma2(bc(w[m][i][u]), wb[m][u], eta0[i]);
+            if ((PM >> m) & 1) eta1[i] = fma2(bc(w[(SHW ? 0 : m)][i][u]), wb[m][u], eta1[i]);
+            else eta0[i] = fma2(bc(w[(SHW ? 0 : m)][i][u]), wb[m][u], eta0[i]);
           }
         }
       }
@@ -344,7 +348,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               if (FAST && u == 1) continue;
-              wg[m][u] = fma2(bc(w[m][i][u]), rr, wg[m][u]);
+              wg[m][u] = fma2(bc(w[(SHW ? 0 : m)][i][u]), rr, wg[m][u]);
             }
           }
         }
@@ -352,10 +356,10 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     };
     using TFast = std::integral_constant<bool, true>;
     using TFull = std::integral_constant<bool, false>;
-    auto load_block = [&](float (&w)[NS][4][4], float (&yv)[4], int r, auto NRtag) {
+    auto load_block = [&](float (&w)[NSL][4][4], float (&yv)[4], int r, auto NRtag) {
       constexpr int NR = decltype(NRtag)::value;
 #pragma unroll
-      for (int m = 0; m < NS; ++m)
+      for (int m = 0; m < NSL; ++m)
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
           const float4 v = *reinterpret_cast<const float4*>(&D.w[m][4 * (r + i)]);
@@ -391,7 +395,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       bool reloaded = false;
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
-        const int first = D.start[m][0];
+        const int first = D.start[(SHW ? 0 : m)][0];
         if (first != cur[m]) {
           flush(m);
           load(m, first, fastmode);
@@ -410,7 +414,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       if (rows == XR) {
         // software pipeline over 4-row blocks: the next block's weights are loaded into a second
         // register set while the current block computes
-        float wa[NS][4][4], wbuf[NS][4][4], ya[4], yb[4];
+        float wa[NSL][4][4], wbuf[NSL][4][4], ya[4], yb[4];
         load_block(wa, ya, 0, N4{});
         if (fastmode) {
 #pragma unroll 1
@@ -427,7 +431,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 #pragma unroll
             for (int m = 0; m < NS; ++m) {
               if ((PM >> m) & 1) {
-                const float4 tw = *reinterpret_cast<const float4*>(tws[s][m]);
+                const float4 tw = *reinterpret_cast<const float4*>(tws[s][(SHW ? 0 : m)]);
                 se1 = fma2(bc(tw.x), wb[m][0], se1);
                 se1 = fma2(bc(tw.z), wb[m][2], se1);
                 se1 = fma2(bc(tw.w), wb[m][3], se1);
@@ -444,18 +448,18 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           }
         }
       } else {
-        float w1[NS][4][4], y1[4];
+        float w1[NSL][4][4], y1[4];
         for (int r = 0; r < rows; ++r) {
           load_block(w1, y1, r, N1{});
           compute_block(w1, y1, N1{}, TFull{});
         }
       }
     } else {
-      float w1[NS][4][4], y1[4];
+      float w1[NSL][4][4], y1[4];
       for (int r = 0; r < rows; ++r) {
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
-          const int sm = D.start[m][r];
+          const int sm = D.start[(SHW ? 0 : m)][r];
           if (sm != cur[m]) change(m, sm);
         }
         load_block(w1, y1, r, N1{});
@@ -528,24 +532,40 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 
 // host ------------------------------------------------------------------------------------------
 template <int FAM, int NS, int PM>
-static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity) {
+static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity, bool shw) {
   // a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps): the kernel's index arithmetic
   // and cooperative loads are written in terms of blockDim.x
   dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff / 2);
-#define LSLB_X2_GO(ST)                                                                                           \
-  do {                                                                                                           \
-    if (unity) {                                                                                                 \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);   \
-      else banded_x2_kernel<FAM, NS, PM, false, true, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);    \
-    } else {                                                                                                     \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);  \
-      else banded_x2_kernel<FAM, NS, PM, false, false, ST><<<grid, block, 0, st>>>(ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra);   \
-    }                                                                                                            \
+  // the shared-band variant pays off for CTAs of up to 8 warps (A/B on one box, H model: 64 chains 0.095 ->
+  // 0.089 ms, 256: 0.230 -> 0.224, 512: 0.380 -> 0.378) and LOSES 1.2 % with the 16-warp CTA of 1024 chains
+  // (0.689 -> 0.697: ptxas schedules the 120-register variant differently), so that one keeps two bands
+  shw = shw && k.tc_eff <= 512;
+#define LSLB_X2_ARGS ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra
+#define LSLB_X2_GO2(ST, SH)                                                                              \
+  do {                                                                                                   \
+    if (unity) {                                                                                         \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);    \
+      else banded_x2_kernel<FAM, NS, PM, false, true, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);     \
+    } else {                                                                                             \
+      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);   \
+      else banded_x2_kernel<FAM, NS, PM, false, false, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);    \
+    }                                                                                                    \
+  } while (0)
+#define LSLB_X2_GO(ST)                                  \
+  do {                                                  \
+    if constexpr (NS == 2) {                            \
+      if (shw) LSLB_X2_GO2(ST, 1);                      \
+      else LSLB_X2_GO2(ST, NS);                         \
+    } else {                                            \
+      LSLB_X2_GO2(ST, NS);                              \
+    }                                                   \
   } while (0)
   if (k.stages >= LSLB_X2_STAGES) LSLB_X2_GO(LSLB_X2_STAGES);
   else if (k.stages == 3) LSLB_X2_GO(3);
   else LSLB_X2_GO(2);
 #undef LSLB_X2_GO
+#undef LSLB_X2_GO2
+#undef LSLB_X2_ARGS
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
 }
@@ -555,25 +575,25 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
   int pm = 0;
   for (int m = 0; m < plan->ns; ++m) pm |= (plan->blk[plan->sp[m]].predictor & 1) << m;
   if (plan->fam == FAM_NORMAL_LS) {
-    if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st, plan->unit_rows)
-                                 : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st, plan->unit_rows);
+    if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st, plan->unit_rows, plan->shared_band)
+                                 : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
     switch (pm) {
-      case 0: return x2_launch<FAM_NORMAL_LS, 2, 0>(ep, k, g, st, plan->unit_rows);
-      case 1: return x2_launch<FAM_NORMAL_LS, 2, 1>(ep, k, g, st, plan->unit_rows);
-      case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st, plan->unit_rows);
-      default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st, plan->unit_rows);
+      case 0: return x2_launch<FAM_NORMAL_LS, 2, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+      case 1: return x2_launch<FAM_NORMAL_LS, 2, 1>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+      case 2: return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+      default: return x2_launch<FAM_NORMAL_LS, 2, 3>(ep, k, g, st, plan->unit_rows, plan->shared_band);
     }
   }
   if (plan->fam == FAM_POISSON) {
-    if (plan->ns == 1) return x2_launch<FAM_POISSON, 1, 0>(ep, k, g, st, plan->unit_rows);
-    return x2_launch<FAM_POISSON, 2, 0>(ep, k, g, st, plan->unit_rows);
+    if (plan->ns == 1) return x2_launch<FAM_POISSON, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+    return x2_launch<FAM_POISSON, 2, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
   }
   if (plan->fam == FAM_BERNOULLI) {
-    if (plan->ns == 1) return x2_launch<FAM_BERNOULLI, 1, 0>(ep, k, g, st, plan->unit_rows);
-    return x2_launch<FAM_BERNOULLI, 2, 0>(ep, k, g, st, plan->unit_rows);
+    if (plan->ns == 1) return x2_launch<FAM_BERNOULLI, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+    return x2_launch<FAM_BERNOULLI, 2, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
   }
-  if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st, plan->unit_rows);
-  return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st, plan->unit_rows);
+  if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+  return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
 }
 
 }  // namespace lslb

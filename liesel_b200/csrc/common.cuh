@@ -225,6 +225,7 @@ struct lslb_plan {
   double lik_const;
   bool rows_sorted;  // every smooth's knot span changes rarely from row to row
   bool unit_rows;    // every spline row's four weights sum to one (x inside the knot range)
+  bool shared_band;  // exactly two smooths whose spans and weights are identical bit for bit (same covariate, same knots)
   float* d_XT;       // tensor-core path (or NULL): plan-owned hi part of the transposed dense block [p x n_pad]
   float *d_XTl, *d_Xh, *d_Xl;  // its lo part; hi/lo parts of X [n x p] (hi + lo == x exactly)
   float* d_tw[LSLB_MAX_SPL];   // float32 banded plans: per 128-row tile the column sums of each smooth's weights

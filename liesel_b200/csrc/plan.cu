@@ -87,6 +87,19 @@ __global__ void unit_rows_kernel(const T* __restrict__ w, long long n, double* o
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// number of rows in which two spline blocks differ (span or any of the four weights, bit for bit)
+__global__ void band_diff_kernel(const int* __restrict__ s0, const int* __restrict__ s1, const float* __restrict__ w0,
+                                 const float* __restrict__ w1, long long n, unsigned long long* out) {
+  unsigned long long cnt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    bool d = s0[i] != s1[i];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) d = d || (__float_as_uint(w0[4 * i + u]) != __float_as_uint(w1[4 * i + u]));
+    cnt += d;
+  }
+  if (cnt) atomicAdd(out, cnt);
+}
+
 // per 128-row tile the sums of the four weight columns of one spline block (one block per tile)
 __global__ void tile_weight_sums_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
   const long long r0 = (long long)blockIdx.x * 128;
@@ -332,6 +345,25 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
       for (int m = 0; m < p->ns; ++m)
         if (!(h[m] <= (desc->dtype == LSLB_F32 ? 2e-6 : 1e-12))) p->unit_rows = false;
       cudaFree(d_mx);
+    }
+  }
+  // two smooths of the same covariate on the same knots (mean and log-sd smooths of a GAMLSS): one band
+  p->shared_band = false;
+  {
+    const char* nos = getenv("LSLB_NO_SHARED_BAND");
+    if (p->ns == 2 && desc->dtype == LSLB_F32 && e == cudaSuccess && !(nos && atoi(nos) != 0) &&
+        p->blk[p->sp[0]].ncoef == p->blk[p->sp[1]].ncoef) {
+      unsigned long long* d_cnt = nullptr;
+      e = cudaMalloc(&d_cnt, sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMemset(d_cnt, 0, sizeof(unsigned long long));
+      if (e == cudaSuccess) {
+        unsigned long long h = 1;
+        band_diff_kernel<<<296, 256>>>(p->blk[p->sp[0]].index, p->blk[p->sp[1]].index,
+                                       (const float*)p->blk[p->sp[0]].data, (const float*)p->blk[p->sp[1]].data, n, d_cnt);
+        e = cudaMemcpy(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost);
+        p->shared_band = e == cudaSuccess && h == 0;
+      }
+      if (d_cnt) cudaFree(d_cnt);
     }
   }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();

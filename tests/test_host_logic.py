@@ -211,8 +211,9 @@ def test_headline_kernel_instantiation_does_not_spill():
     if not os.path.exists(log):
         pytest.skip("no build log (the library was not built in this tree)")
     text = open(log).read()
-    key = "banded_x2_kernelILi0ELi2ELi2ELb1ELb1ELi6E"  # <FAM_NORMAL_LS, NS=2, PM=2, GRAD, UNITY, 6 stages>
-    i = text.index("Function properties for _ZN4lslb16" + key)
-    block = text[i: i + 400]
-    assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in block, block
-    assert "Used 128 registers" in block or "Used 12" in block
+    # <FAM_NORMAL_LS, NS=2, PM=2, GRAD, UNITY, 6 stages, bands loaded: 1 (shared covariate, H) and 2>
+    for key in ("banded_x2_kernelILi0ELi2ELi2ELb1ELb1ELi6ELi1E", "banded_x2_kernelILi0ELi2ELi2ELb1ELb1ELi6ELi2E"):
+        i = text.index("Function properties for _ZN4lslb16" + key)
+        block = text[i: i + 400]
+        assert "0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads" in block, block
+        assert "Used 12" in block or "Used 11" in block
