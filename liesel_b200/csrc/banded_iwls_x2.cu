@@ -30,11 +30,13 @@ struct IwRaw {
 //        take the three-term form of banded_x2.cu (b_u - b_1 against w_u, u != 1).
 // Packed ops per row and chain pair (Normal location-scale, location target): forward 6 (8 without
 // UNITY), d / z / r / W 4, score 4, Gram 10 (14 without PAIRS) = 24 (31 before round 2).
-template <int FAM, int NS, int PM, int TK, int TM, int TP, bool PAIRS, bool UNITY>
+// NSL: bands staged (1 = both smooths share spans and weights: same covariate, same knots; see banded_x2.cu)
+template <int FAM, int NS, int PM, int TK, int TM, int TP, bool PAIRS, bool UNITY, int NSL = NS>
 __global__ void __launch_bounds__(128, 4)
 banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /*p of target*/,
                       int nq, float* __restrict__ partial, int tiles_per_cta, int ntiles_total, int tiles_extra) {
-  __shared__ __align__(128) IwRaw<NS, PAIRS> raw[XSTAGES];
+  constexpr bool SHW = NSL < NS;
+  __shared__ __align__(128) IwRaw<NSL, PAIRS> raw[XSTAGES];
   __shared__ __align__(8) u64 full[XSTAGES];
   const int tid = threadIdx.x;
   const int c = 2 * (blockIdx.x * blockDim.x + tid);
@@ -65,13 +67,13 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
   };
   auto issue = [&](int t, int s) {
     const long long r0 = (long long)t * XR;
-    constexpr unsigned bytes = XR * 4 + NS * (XR * 16 + XR * 4) + (PAIRS ? XR * 48 : 0);
+    constexpr unsigned bytes = XR * 4 + NSL * (XR * 16 + XR * 4) + (PAIRS ? XR * 48 : 0);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(x_smem_u32(&full[s])),
                  "r"(bytes)
                  : "memory");
     bulk(raw[s].x.y, p.y + r0, XR * 4, &full[s]);
 #pragma unroll
-    for (int m = 0; m < NS; ++m) {
+    for (int m = 0; m < NSL; ++m) {
       bulk(raw[s].x.w[m], p.sp[m].w + 4 * r0, XR * 16, &full[s]);
       bulk(raw[s].x.start[m], p.sp[m].start + r0, XR * 4, &full[s]);
     }
@@ -180,7 +182,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
       const int kn = k + XSTAGES - 1;
       if (tid == 0 && kn < my_tiles && tile_rows(tile0 + kn) == XR) issue(tile0 + kn, kn % XSTAGES);
     }
-    XRaw<NS>& D = raw[s].x;
+    XRaw<NSL>& D = raw[s].x;
     const float* WP = raw[s].wp;
     if (rows == XR) {
       wait_full(s, (k / XSTAGES) & 1);
@@ -189,7 +191,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
       for (int r = tid; r < rows; r += blockDim.x) {
         D.y[r] = p.y[r0 + r];
 #pragma unroll
-        for (int m = 0; m < NS; ++m) {
+        for (int m = 0; m < NSL; ++m) {
           D.start[m][r] = p.sp[m].start[r0 + r];
 #pragma unroll
           for (int u = 0; u < 4; ++u) D.w[m][4 * r + u] = p.sp[m].w[4 * (r0 + r) + u];
@@ -203,7 +205,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
     }
     bool uni = true;
 #pragma unroll
-    for (int m = 0; m < NS; ++m) {
+    for (int m = 0; m < NSL; ++m) {
       const int first = D.start[m][0];
       bool eq = true;
       for (int r = (tid & 31); r < rows; r += 32) eq = eq && (D.start[m][r] == first);
@@ -212,17 +214,20 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
 
     auto row = [&](int r, auto FASTtag) {
       constexpr bool FAST = decltype(FASTtag)::value;
-      float w[NS][4];
+      float w[NSL][4];
       u64 eta0 = FAST ? e0i : o0, eta1 = FAST ? e1i : o1;
 #pragma unroll
-      for (int m = 0; m < NS; ++m) {
+      for (int m = 0; m < NSL; ++m) {
         const float4 v = *reinterpret_cast<const float4*>(&D.w[m][4 * r]);
         w[m][0] = v.x; w[m][1] = v.y; w[m][2] = v.z; w[m][3] = v.w;
+      }
+#pragma unroll
+      for (int m = 0; m < NS; ++m) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (FAST && u == 1) continue;
-          if ((PM >> m) & 1) eta1 = fma2(bc(w[m][u]), wb[m][u], eta1);
-          else eta0 = fma2(bc(w[m][u]), wb[m][u], eta0);
+          if ((PM >> m) & 1) eta1 = fma2(bc(w[SHW ? 0 : m][u]), wb[m][u], eta1);
+          else eta0 = fma2(bc(w[SHW ? 0 : m][u]), wb[m][u], eta0);
         }
       }
       const u64 d = fma2(eta0, NEG1, bc(D.y[r]));
@@ -246,7 +251,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
       }
       if constexpr (TK == 0) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) ts[a] = fma2(bc(w[TM][a]), rr, ts[a]);
+        for (int a = 0; a < 4; ++a) ts[a] = fma2(bc(w[SHW ? 0 : TM][a]), rr, ts[a]);
         if constexpr (PAIRS) {
           const float4 p0 = *reinterpret_cast<const float4*>(&WP[12 * r]);
           const float4 p1 = *reinterpret_cast<const float4*>(&WP[12 * r + 4]);
@@ -257,13 +262,13 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
         } else {
           u64 wa[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) wa[a] = mul2(bc(w[TM][a]), W);
+          for (int a = 0; a < 4; ++a) wa[a] = mul2(bc(w[SHW ? 0 : TM][a]), W);
           int u = 0;
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = a; b < 4; ++b) {
-              tg[u] = fma2(bc(w[TM][b]), wa[a], tg[u]);
+              tg[u] = fma2(bc(w[SHW ? 0 : TM][b]), wa[a], tg[u]);
               ++u;
             }
         }
@@ -288,7 +293,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
       bool reloaded = false;
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
-        const int first = D.start[m][0];
+        const int first = D.start[SHW ? 0 : m][0];
         if (first != cur[m]) {
           change(m, first, fastmode);
           reloaded = true;
@@ -314,7 +319,7 @@ banded_iwls_x2_kernel(const __grid_constant__ EvalParams<float> p, int tp_rows /
       for (int r = 0; r < rows; ++r) {
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
-          const int sm = D.start[m][r];
+          const int sm = D.start[SHW ? 0 : m][r];
           if (sm != cur[m]) change(m, sm, false);
         }
         row(r, TFull{});
@@ -336,16 +341,27 @@ static int iwx2_go(const EvalParams<float>& ep, int p, int nq, float* partial, c
                    cudaStream_t st) {
   dim3 grid(k.ntiles_chain, k.nchunks), block(128);
   const bool pairs = TK == 0 && ep.sp[TM].wp != nullptr;
-  const bool unity = k.stages != 0;  // banded_iwls_cfg: plan->unit_rows
-#define LSLB_IW_GO(PR, UN)                                                                         \
-  banded_iwls_x2_kernel<FAM, NS, PM, TK, TM, TP, PR, UN><<<grid, block, 0, st>>>(ep, p, nq, partial, \
-                                                                                 k.tiles_per_cta, k.ntiles_total, k.tiles_extra)
+  const bool unity = (k.stages & 1) != 0;  // banded_iwls_cfg: bit 0 plan->unit_rows, bit 1 plan->shared_band
+  const bool shw = (k.stages & 2) != 0;
+#define LSLB_IW_GO2(PR, UN, NL)                                                                        \
+  banded_iwls_x2_kernel<FAM, NS, PM, TK, TM, TP, PR, UN, NL><<<grid, block, 0, st>>>(ep, p, nq, partial,  \
+                                                                                     k.tiles_per_cta, k.ntiles_total, k.tiles_extra)
+#define LSLB_IW_GO(PR, UN)                      \
+  do {                                          \
+    if constexpr (NS == 2) {                    \
+      if (shw) LSLB_IW_GO2(PR, UN, 1);          \
+      else LSLB_IW_GO2(PR, UN, NS);             \
+    } else {                                    \
+      LSLB_IW_GO2(PR, UN, NS);                  \
+    }                                           \
+  } while (0)
   if constexpr (TK == 0) {
     if (pairs) { if (unity) LSLB_IW_GO(true, true); else LSLB_IW_GO(true, false); }
     else { if (unity) LSLB_IW_GO(false, true); else LSLB_IW_GO(false, false); }
   } else {
     if (unity) LSLB_IW_GO(false, true); else LSLB_IW_GO(false, false);
   }
+#undef LSLB_IW_GO2
 #undef LSLB_IW_GO
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
@@ -397,7 +413,8 @@ BandedCfg banded_iwls_cfg(const lslb_plan* plan, int C) {
   k.ntiles_chain = k.Cpad / k.TC;
   k.ntiles_total = (int)((plan->desc.n + XR - 1) / XR);
   if (k.ntiles_total < 1) k.ntiles_total = 1;
-  k.stages = plan->unit_rows ? 1 : 0;  // this kernel's ring depth is fixed (XSTAGES); the field carries UNITY
+  // this kernel's ring depth is fixed (XSTAGES); the field carries the two plan flags
+  k.stages = (plan->unit_rows ? 1 : 0) | (plan->shared_band ? 2 : 0);
   long long want = ((long long)plan->sm_count * 4 + k.ntiles_chain - 1) / k.ntiles_chain;
   if (want > k.ntiles_total) want = k.ntiles_total;
   if (want < 1) want = 1;
