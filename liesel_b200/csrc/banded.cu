@@ -336,11 +336,25 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   if (k.ntiles_total < 1) k.ntiles_total = 1;
   int ctas_per_sm = x2 ? 16 / (k.tc_eff / 64) : 6;  // x2: at most 16 resident warps per SM (registers)
   if (x2) {
-    // shared memory: 5.7 KB per ring stage. 16 one-warp CTAs take 2 stages each, 8 two-warp CTAs 3, the
-    // rest 6 (until round 2 every CTA had 6 stages = 34 KB, which capped an SM at 6 CTAs: 6 warps at
-    // 64 chains, 12 at 128)
+    // 2..8 chain warps per chain tile (65..512 chains) on a plan whose two smooths share their band: ONE phased
+    // CTA per SM - the 16 warps split into 2 / 4 / 8 row phases that take the tiles of one TMA ring in turn
+    // (banded_x2.cu). A/B on one box, H model, ms per call against the several-small-CTAs launch of round 2:
+    // 128 chains 0.134 -> 0.130, 256: 0.224 -> 0.211, 512: 0.378 -> 0.370; at 64 chains (16 one-warp phases)
+    // it loses 2 %, and the two-band instantiation spills (150 B) and loses 2-7 %, so those keep the small
+    // CTAs (ring of 6 / 3 / 2 stages for 34 / 17 / 11 KB CTAs). LSLB_X2_NO_PHASES=1 disables it for A/B runs.
+    static const bool no_phases = [] {
+      const char* e = getenv("LSLB_X2_NO_PHASES");
+      return e && atoi(e) != 0;
+    }();
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     k.stages = ctas_per_sm >= 16 ? 2 : (ctas_per_sm >= 8 ? 3 : 6);
+    if (!no_phases && plan->shared_band && plan->ns == 2 && ctas_per_sm >= 2 && ctas_per_sm <= 8) {
+      int ph = 1;
+      while (ph * 2 <= ctas_per_sm) ph *= 2;  // power of two: the ring depth (16) must be a multiple of it
+      k.phases = ph;
+      k.stages = 16;
+      ctas_per_sm = 1;
+    }
   } else if (ctas_per_sm > 5) {
     ctas_per_sm = 5;  // shared memory of the scalar kernel's row stages
   }
@@ -361,6 +375,7 @@ BandedCfg banded_cfg(const lslb_plan* plan, int C) {
   k.nchunks = (int)want;
   k.tiles_per_cta = k.ntiles_total / k.nchunks;
   k.tiles_extra = k.ntiles_total % k.nchunks;
+  k.nchunks *= k.phases;  // partial slots: one per CTA and row phase
   return k;
 }
 

@@ -52,24 +52,61 @@ __device__ __forceinline__ unsigned x2_smid() {
 // SHW: both smooths are splines of the SAME covariate on the same knots (H / S3: mean and log-sd smooths of
 // one x; checked bit for bit at plan creation): one copy of the weights and spans is staged and held in
 // registers for both (32 registers and half of the shared-memory loads of the hot loop).
-template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S, int NSL = NS>  // NSL: bands loaded (1 = shared)
+// PHASED (at most 8 chain warps per chain tile, i.e. up to 512 chains): the SM holds ONE CTA of ~16 warps, split
+// into nph = 2 / 4 / 8 / 16 row PHASES of cw chain warps each. Tile k of the CTA's row range is evaluated by
+// the warps of phase k mod nph only, and every phase writes its own partial slot. X2S is a multiple of nph,
+// so a ring stage always serves the same phase (the parity wait on its mbarrier cannot alias a use by
+// another phase) and each phase refills its own stages: in effect nph rings of X2S / nph stages, launched
+// and retired together. Replaces the several small CTAs per SM of round 2 (A/B in DESIGN section 4).
+template <int NSL, int X2S, bool PHASED>
+struct X2Smem {
+  XRaw<NSL> raw[X2S + (PHASED ? 1 : 0)];  // PHASED: one more tile buffer for the ragged last tile of the data
+  u64 full[X2S];
+  int done[X2S];  // warps that have finished with the tile in stage s
+  alignas(16) float tws[X2S][NSL][4];  // the tile's weight-column sums (plan constant)
+};
+extern __shared__ __align__(128) unsigned char x2_dyn_smem[];
+
+template <int FAM, int NS, int PM, bool GRAD, bool UNITY, int X2S, int NSL = NS, bool PHASED = false>  // NSL: bands loaded (1 = shared)
 #ifndef LSLB_X2_NRB
 #define LSLB_X2_NRB 4   // rows per register block (4 or 2)
 #endif
 #ifndef LSLB_X2_STAGES
 #define LSLB_X2_STAGES 6  // ring depth: how many tiles the fastest warp of a CTA may run ahead of the slowest
 #endif
-__global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA (or 2 x 8, 4 x 4 for few chains)
-banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total, int tiles_extra) {
+__global__ void __launch_bounds__(512, 1)  // 16 warps per SM in ONE CTA
+banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta, int ntiles_total, int tiles_extra,
+                 int cw /* PHASED: chain warps per phase */, int nph /* PHASED: row phases */) {
   constexpr bool SHW = NSL < NS;
-  __shared__ __align__(128) XRaw<NSL> raw[X2S];
-  __shared__ __align__(8) u64 full[X2S];
-  __shared__ int done[X2S];  // warps that have finished with the tile in stage s
-  __shared__ __align__(16) float tws[X2S][NSL][4];  // the tile's weight-column sums (plan constant)
+  X2Smem<NSL, X2S, PHASED>* smp;
+  if constexpr (PHASED) {  // 16- and 32-stage rings: beyond the 48 KB of static shared memory
+    smp = reinterpret_cast<X2Smem<NSL, X2S, PHASED>*>(x2_dyn_smem);
+  } else {
+    __shared__ __align__(128) X2Smem<NSL, X2S, false> sm_static;
+    smp = &sm_static;
+  }
+  XRaw<NSL>* const raw = smp->raw;
+  u64* const full = smp->full;
+  int* const done = smp->done;
+  float (*const tws)[NSL][4] = smp->tws;
 
   const int tid = threadIdx.x;
-  const int c = 2 * (blockIdx.x * blockDim.x + tid);  // first of this thread's two chains (< Cpad)
-  const int ch = blockIdx.y;
+  // c: first of this thread's two chains (< Cpad); ch: partial slot; cy: the CTA's row chunk; k0: first tile
+  // (cw and nph are read from the parameter bank where they are used and the phase index is recomputed in the
+  //  rare ragged-tile branch: the hot instantiations sit at the 128-register cap)
+  const int cy = blockIdx.y;
+  int c, ch, k0 = 0;
+  if constexpr (PHASED) {
+    const int warp = tid >> 5;
+    const int ph = warp / cw;
+    c = 2 * ((blockIdx.x * cw + (warp - ph * cw)) * 32 + (tid & 31));
+    ch = cy * nph + ph;
+    k0 = ph;
+  } else {
+    c = 2 * (blockIdx.x * blockDim.x + tid);
+    ch = cy;
+  }
+  (void)k0; (void)nph; (void)cw;
   // balanced partition of the tiles over the row chunks (chunk sizes differ by at most one tile; with
   // ceil(T / CTAs) tiles per CTA the last SMs of a 4-CTAs-per-SM launch held 3 CTAs and the others
   // carried 56 tiles instead of 52.8)
@@ -78,8 +115,8 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
   // it spill - 5 % on H.)
   // (written as ONE multiply of the block index by a selected constant: the hot instantiation sits at
   //  128 registers and spilled - 5 % on H - with min(ch, extra) or a 64-bit division here)
-  const int tpa = ch < tiles_extra ? tiles_per_cta + 1 : tiles_per_cta;
-  const int tile0 = ch * tpa + (ch < tiles_extra ? 0 : tiles_extra);
+  const int tpa = cy < tiles_extra ? tiles_per_cta + 1 : tiles_per_cta;
+  const int tile0 = cy * tpa + (cy < tiles_extra ? 0 : tiles_extra);
   const int my_tiles = tpa;
   (void)ntiles_total;
 #ifdef LSLB_X2_TRACE
@@ -226,17 +263,21 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     load(m, s, false);
   };
 
-  for (int k = 0; k < my_tiles; ++k) {
+  for (int k = k0; k < my_tiles; k += PHASED ? nph : 1) {
     const int t = tile0 + k;
     const int s = k % X2S;
     const int rows = tile_rows(t);
-    XRaw<NSL>& D = raw[s];
+    // PHASED: the ragged tile (the last tile of the data, one per launch and chain tile) has its own buffer
+    XRaw<NSL>& D = raw[(PHASED && rows != XR) ? X2S : s];
     if (rows == XR) {
       wait_full(s, (k / X2S) & 1);
     } else {  // ragged last tile of the data: ordinary loads (bulk copies need 16-byte multiples)
-      __syncthreads();  // every warp has left the tile that used this stage before
+      // not PHASED: every warp has left the tile that used this stage before
+      if constexpr (!PHASED) __syncthreads();
       const long long r0 = (long long)t * XR;
-      for (int r = tid; r < rows; r += blockDim.x) {
+      const int ph = PHASED ? (tid >> 5) / cw : 0;
+      const int tq = PHASED ? tid - ph * cw * 32 : tid, nq = PHASED ? cw * 32 : (int)blockDim.x;
+      for (int r = tq; r < rows; r += nq) {
         D.y[r] = p.y[r0 + r];
 #pragma unroll
         for (int m = 0; m < NSL; ++m) {
@@ -245,7 +286,12 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
           for (int u = 0; u < 4; ++u) D.w[m][4 * r + u] = p.sp[m].w[4 * (r0 + r) + u];
         }
       }
-      __syncthreads();
+      if constexpr (PHASED) {  // the warps of this phase only (named barrier 1 + ph; one warp: __syncwarp)
+        if (cw > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + ph), "r"(cw * 32) : "memory");
+        else __syncwarp();
+      } else {
+        __syncthreads();
+      }
     }
 
     // is every smooth's span constant over this tile? (each warp evaluates it redundantly)
@@ -497,7 +543,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     __syncwarp();
     if ((tid & 31) == 0) {
       __threadfence_block();
-      if (atomicAdd(&done[s], 1) == (int)(blockDim.x >> 5) - 1) {
+      if (atomicAdd(&done[s], 1) == (PHASED ? cw : (int)(blockDim.x >> 5)) - 1) {
         done[s] = 0;
         const int kn = k + X2S;
         if (kn < my_tiles && tile_rows(tile0 + kn) == XR) {
@@ -533,38 +579,54 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
 // host ------------------------------------------------------------------------------------------
 template <int FAM, int NS, int PM>
 static int x2_launch(const EvalParams<float>& ep, const BandedCfg& k, bool g, cudaStream_t st, bool unity, bool shw) {
-  // a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps): the kernel's index arithmetic
-  // and cooperative loads are written in terms of blockDim.x
-  dim3 grid(k.ntiles_chain, k.nchunks), block(k.tc_eff / 2);
-  // the shared-band variant pays off for CTAs of up to 8 warps (A/B on one box, H model: 64 chains 0.095 ->
+  // Not phased: a CTA owns tc_eff chains = tc_eff / 2 threads (whole warps). Phased: cw = tc_eff / 64 chain
+  // warps x k.phases row phases, one partial slot per phase (k.nchunks = CTAs x phases).
+  const int cw = k.tc_eff / 64;
+  dim3 grid(k.ntiles_chain, k.nchunks / k.phases), block(k.tc_eff / 2 * k.phases);
+  // the shared-band variant pays off for CTAs of up to 8 chain warps (A/B on one box, H model: 64 chains 0.095 ->
   // 0.089 ms, 256: 0.230 -> 0.224, 512: 0.380 -> 0.378) and LOSES 1.2 % with the 16-warp CTA of 1024 chains
   // (0.689 -> 0.697: ptxas schedules the 120-register variant differently), so that one keeps two bands
   shw = shw && k.tc_eff <= 512;
-#define LSLB_X2_ARGS ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra
-#define LSLB_X2_GO2(ST, SH)                                                                              \
-  do {                                                                                                   \
-    if (unity) {                                                                                         \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, true, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);    \
-      else banded_x2_kernel<FAM, NS, PM, false, true, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);     \
-    } else {                                                                                             \
-      if (g) banded_x2_kernel<FAM, NS, PM, true, false, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);   \
-      else banded_x2_kernel<FAM, NS, PM, false, false, ST, SH><<<grid, block, 0, st>>>(LSLB_X2_ARGS);    \
-    }                                                                                                    \
+#define LSLB_X2_ARGS ep, k.tiles_per_cta, k.ntiles_total, k.tiles_extra, cw, k.phases
+#define LSLB_X2_GO3(GR, UN, ST, SH, PHS)                                                   \
+  do {                                                                                     \
+    auto kern = banded_x2_kernel<FAM, NS, PM, GR, UN, ST, SH, PHS>;                        \
+    size_t dyn = 0;                                                                        \
+    if (PHS) {                                                                             \
+      dyn = sizeof(X2Smem<SH, ST, PHS>);                                                   \
+      LSLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+    }                                                                                      \
+    kern<<<grid, block, dyn, st>>>(LSLB_X2_ARGS);                                          \
+  } while (0)
+#define LSLB_X2_GO2(ST, SH, PHS)                                    \
+  do {                                                              \
+    if (unity) {                                                    \
+      if (g) LSLB_X2_GO3(true, true, ST, SH, PHS);                  \
+      else LSLB_X2_GO3(false, true, ST, SH, PHS);                   \
+    } else {                                                        \
+      if (g) LSLB_X2_GO3(true, false, ST, SH, PHS);                 \
+      else LSLB_X2_GO3(false, false, ST, SH, PHS);                  \
+    }                                                               \
   } while (0)
 #define LSLB_X2_GO(ST)                                  \
   do {                                                  \
     if constexpr (NS == 2) {                            \
-      if (shw) LSLB_X2_GO2(ST, 1);                      \
-      else LSLB_X2_GO2(ST, NS);                         \
+      if (shw) LSLB_X2_GO2(ST, 1, false);               \
+      else LSLB_X2_GO2(ST, NS, false);                  \
     } else {                                            \
-      LSLB_X2_GO2(ST, NS);                              \
+      LSLB_X2_GO2(ST, NS, false);                       \
     }                                                   \
   } while (0)
-  if (k.stages >= LSLB_X2_STAGES) LSLB_X2_GO(LSLB_X2_STAGES);
+  if (k.phases > 1) {
+    // phased CTAs: shared-band plans only (banded_cfg); ring of 16 stages = a multiple of 2, 4 and 8 phases
+    if constexpr (NS == 2) LSLB_X2_GO2(16, 1, true);
+    else return LSLB_ERR_INVALID;
+  } else if (k.stages >= LSLB_X2_STAGES) LSLB_X2_GO(LSLB_X2_STAGES);
   else if (k.stages == 3) LSLB_X2_GO(3);
   else LSLB_X2_GO(2);
 #undef LSLB_X2_GO
 #undef LSLB_X2_GO2
+#undef LSLB_X2_GO3
 #undef LSLB_X2_ARGS
   LSLB_LAUNCH_CHECK();
   return LSLB_OK;
@@ -574,6 +636,9 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
                      cudaStream_t st) {
   int pm = 0;
   for (int m = 0; m < plan->ns; ++m) pm |= (plan->blk[plan->sp[m]].predictor & 1) << m;
+#ifdef LSLB_X2_DEV  // development builds: the H / S3 instantiations only (the full file takes minutes to compile)
+  return x2_launch<FAM_NORMAL_LS, 2, 2>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+#else
   if (plan->fam == FAM_NORMAL_LS) {
     if (plan->ns == 1) return pm ? x2_launch<FAM_NORMAL_LS, 1, 1>(ep, k, g, st, plan->unit_rows, plan->shared_band)
                                  : x2_launch<FAM_NORMAL_LS, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
@@ -594,6 +659,7 @@ int launch_banded_x2(const lslb_plan* plan, const EvalParams<float>& ep, const B
   }
   if (plan->ns == 1) return x2_launch<FAM_NORMAL_FIXED, 1, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
   return x2_launch<FAM_NORMAL_FIXED, 2, 0>(ep, k, g, st, plan->unit_rows, plan->shared_band);
+#endif
 }
 
 }  // namespace lslb

@@ -269,6 +269,7 @@ struct BandedCfg {
   int tc_eff = 0;  // banded_x2: chains a CTA really owns (multiple of 64, <= TC); 0 = TC
   int tiles_extra = 0;  // the first tiles_extra row chunks take tiles_per_cta + 1 tiles (balanced partition)
   int stages = 6;  // banded_x2: depth of the TMA ring (6; 3 / 2 for the 2- / 1-warp CTAs of small chain counts)
+  int phases = 1;  // banded_x2 / banded_iwls_x2, phased CTAs: row phases per CTA; nchunks counts partial slots = CTAs x phases
 };
 struct TcCfg {
   int Cpad, ntiles_chain, ntiles_rows, nkchunks, tiles_per_cta, kchunks_per_cta, nchunks;
