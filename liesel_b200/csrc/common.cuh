@@ -283,6 +283,10 @@ TcCfg dense_tc_cfg(const lslb_plan* plan, int C);
 size_t dense_tc_rt_floats(const lslb_plan* plan, int C);
 int launch_dense_tc(const lslb_plan* plan, const TcCfg& k, int C, const float* params, float* RT,
                     float* partial, bool want_grad, cudaStream_t st);
+bool tiny_eligible(const lslb_plan* plan, int C);  // tiny.cu: small regressions, one launch per call
+template <typename T>
+int launch_tiny(const lslb_plan* plan, const EvalParams<T>& ep, const FinalizeParams& fp, int C, const T* params,
+                T* logp, T* grad, cudaStream_t st);
 bool dgroup_x2_eligible(const lslb_plan* plan);  // dgroup_x2.cu
 LaunchCfg dgroup_x2_cfg(const lslb_plan* plan, int C);
 int launch_dgroup_x2(const lslb_plan* plan, const EvalParams<float>& ep, const LaunchCfg& k,

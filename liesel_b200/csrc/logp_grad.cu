@@ -731,7 +731,14 @@ int launch_logp_grad(const lslb_plan* plan, int C, const T* params, const T* aux
   size_t smem = (fast || dense || dgrp || tcp || msm || msr) ? 0 : eval_smem_per_chain(plan) * k.TC + eval_smem_fixed(plan);
   if (smem > 200 * 1024) return LSLB_ERR_UNSUPPORTED;
   WsLayout<T> L = layout_ws<T>(plan, k, ws);
-  if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;
+  if (L.bytes > ws_bytes) return LSLB_ERR_WORKSPACE;  // (the ABI's contract, also where the workspace stays unused)
+  if (tiny_eligible(plan, C)) {  // small regression: everything in one launch, workspace untouched (tiny.cu)
+    FinalizeParams fpt;
+    fill_finalize_params(plan, fpt, C, C, 1, flags);
+    EvalParams<T> ept;
+    fill_eval_params<T>(plan, ept, C, C);
+    return launch_tiny<T>(plan, ept, fpt, C, params, logp, grad, stream);
+  }
 
   FinalizeParams fp;
   fill_finalize_params(plan, fp, C, k.Cpad, k.nchunks, flags);
@@ -821,6 +828,7 @@ template int launch_logp_grad<double>(const lslb_plan*, int, const double*, cons
 extern "C" const char* lslb_plan_kernel_name(const lslb_plan* plan, int C) {
   using namespace lslb;
   if (!plan || C < 1) return "";
+  if (tiny_eligible(plan, C)) return "lslb::tiny_kernel";
   if (dense_tc_eligible(plan, C)) return "lslb::dense_tc_k1 + lslb::dense_tc_k2";
   if (dense_x2_eligible(plan)) return "lslb::dense_x2_kernel";
   if (dgroup_x2_eligible(plan)) return "lslb::dgroup_x2_kernel";

@@ -382,7 +382,8 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
                       : (msmooth_x2_eligible(p) ? "multi_smooth_x2" : "banded_runlength");
   } else if (p->ns == 0 && p->nd == 1 && p->blk[p->dn[0]].ncoef <= 16) {
     p->variant = VAR_DENSE_REG;
-    p->variant_name = dgroup_x2_eligible(p) ? "dense_group_x2_tma" : "dense_registers";
+    p->variant_name = dgroup_x2_eligible(p) ? "dense_group_x2_tma"
+                      : (tiny_eligible(p, 1) ? "dense_single_launch" : "dense_registers");
   } else {
     p->variant = VAR_GENERIC;
     p->variant_name = dense_x2_eligible(p) ? "dense_x2_register_sliced" : "generic_smem";

@@ -222,6 +222,50 @@ def test_bitwise_reproducible(lb):
     assert torch.equal(l1, l2) and torch.equal(g1, g2)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("family", ["normal", "bernoulli", "poisson"])
+def test_single_launch_kernel_against_oracle_and_general_path(lb, dtype, family):
+    """Small regressions (S1-like: n <= 4095 rows, rows x chains <= 2^20) run lslb::tiny_kernel, one launch per
+    call. Oracle parity per family and dtype, agreement with the three-launch general path (taken by the same
+    plan when rows x chains exceeds the bound), value-only calls, bitwise reproducibility."""
+    rng = np.random.default_rng(11)
+    n, p = 1000, 10
+    X = np.column_stack([np.ones(n), rng.uniform(size=(n, p - 1))]).astype(dtype)
+    beta = np.linspace(-1, 1, p) * (0.3 if family != "normal" else 1.0)
+    eta = X.astype(np.float64) @ beta
+    if family == "normal":
+        spec, centre = synth.s1_blr(n=n, p=p, dtype=dtype)
+    else:
+        from liesel_b200.spec import ModelSpec
+
+        y = rng.binomial(1, 1 / (1 + np.exp(-eta))) if family == "bernoulli" else rng.poisson(np.exp(eta))
+        spec = ModelSpec(dtype=np.dtype(dtype))
+        pred = "logits" if family == "bernoulli" else "log_rate"
+        spec.add_response(y.astype(np.float64), family).add_predictor(pred)
+        spec.add_p_smooth(X[:, 1:], 0.0, 10.0, pred, pred + "_p0")
+        spec.add_p_smooth(np.ones((n, 1), dtype=dtype), 0.5, 100.0, pred, pred + "_icpt")
+        centre = np.concatenate([beta[1:], beta[:1]])
+    plan = lb.Plan(spec)
+    assert plan.kernel_name(4) == "lslb::tiny_kernel", plan.kernel_name(4)
+    C = 6
+    th, aux = synth.evaluation_points(spec, centre, C)
+    check_logp_grad(spec, plan, th, aux)
+    t = dev(th, plan)
+    l1, g1 = plan.logp_grad(t)
+    l1, g1 = l1.clone(), g1.clone()
+    l2, g2 = plan.logp_grad(t)
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    # the same plan on 2048 chains leaves the single-launch bound: first chains must agree
+    Cb = 2048
+    assert plan.kernel_name(Cb) != "lslb::tiny_kernel"
+    thb = np.concatenate([th, np.tile(th[:1], (Cb - C, 1))])
+    lbig, gbig = plan.logp_grad(dev(thb, plan))
+    tol = 2e-5 if dtype == np.float32 else 1e-11
+    np.testing.assert_allclose(lbig[:C].cpu().numpy(), l1.cpu().numpy(), rtol=tol)
+    scale = np.abs(g1.cpu().numpy()).max()
+    np.testing.assert_allclose(gbig[:C].cpu().numpy(), g1.cpu().numpy(), rtol=tol * 10, atol=tol * 10 * scale)
+
+
 def test_tiny_and_empty_inputs(lb):
     for n in [1, 2, 31, 33]:
         spec, centre = synth.s3_gamlss(n=max(n, 8), k=8, dtype=np.float64)
