@@ -174,6 +174,26 @@ int lslb_iwls_f64(const lslb_plan* plan, int C, int block, const double* params,
                   const double* aux, double* score, double* info, double* chol,
                   uint32_t flags, void* ws, size_t ws_bytes, lslb_stream_t stream);
 
+/*
+ * IWLS quantities of the RANDOM-INTERCEPT block for C chains (models with one group block next to at
+ * most one dense block of <= 16 columns and intercepts: the S5 family). The reference's IWLSKernel would
+ * form the dense G x G matrix -jacfwd(grad(log_prob)) (iwls.py:218-243); for b[idx[i]] it is diagonal:
+ *   score     [C x G] = d logp / d b                      (iwls.py:206-216,315)
+ *   info_diag [C x G] = diagonal of -d2 logp / d b^2 = per-group sum of the observed information weights
+ *                       + 1 / s^2 of the Normal prior, WITHOUT the ridge (iwls.py:232)
+ *   loglik_group [C x G] or NULL = the group's share of the log-posterior as a function of b_g: sum of its
+ *                       rows' log-likelihood terms (without the row constants) - (b_g - m)^2 / (2 s^2).
+ *                       Given the other blocks the posterior of b factorises over the groups, so these
+ *                       are what a group-by-group Metropolis-Hastings step needs (iwls_sampler.py).
+ * No workspace. LSLB_SKIP_PRIOR leaves the prior terms out (row-sharded ranks > 0).
+ */
+int lslb_iwls_group_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
+                        float* score, float* info_diag, float* loglik_group, uint32_t flags,
+                        lslb_stream_t stream);
+int lslb_iwls_group_f64(const lslb_plan* plan, int C, const double* params, const double* aux,
+                        double* score, double* info_diag, double* loglik_group, uint32_t flags,
+                        lslb_stream_t stream);
+
 /* Ridge + batched Cholesky alone (for info summed across ranks): chol may alias info. */
 int lslb_chol_f32(int C, int p, const float* info, float* chol, lslb_stream_t stream);
 int lslb_chol_f64(int C, int p, const double* info, double* chol, lslb_stream_t stream);
@@ -213,6 +233,25 @@ int lslb_iwls_propose_f64(int C, int p, const double* beta, const double* score,
                           const double* chol, const double* step, const double* z,
                           const double* x_eval, double* prop, double* logq,
                           lslb_stream_t stream);
+
+/*
+ * The same proposal tail for a DIAGONAL information matrix (random-intercept block; info_diag from
+ * lslb_iwls_group_*): chol = diag(sqrt(info_diag + 1e-6 * mean(info_diag))) (ridge of iwls.py:233-238);
+ * when an entry is not positive and finite the factor is NaN as a whole in the reference and
+ * IWLSKernel._safe_chol falls back to the identity with error code 2 (iwls.py:245-290): code [C] (or NULL)
+ * receives 2 for such chains, 0 otherwise. beta, score, info_diag, z, x_eval, prop are [C x p].
+ * logq_elem [C x p] or NULL receives the summands of logq (one univariate normal log-density per entry).
+ * local_ridge != 0: entry j is ridged by 1e-6 of ITSELF instead of 1e-6 of the mean, so that the proposal
+ * of an entry depends on that entry alone (group-by-group acceptance; not a reference mode).
+ */
+int lslb_iwls_propose_diag_f32(int C, int p, const float* beta, const float* score,
+                               const float* info_diag, const float* step, const float* z,
+                               const float* x_eval, float* prop, float* logq, int* code,
+                               float* logq_elem, int local_ridge, lslb_stream_t stream);
+int lslb_iwls_propose_diag_f64(int C, int p, const double* beta, const double* score,
+                               const double* info_diag, const double* step, const double* z,
+                               const double* x_eval, double* prop, double* logq, int* code,
+                               double* logq_elem, int local_ridge, lslb_stream_t stream);
 
 /*
  * Banded cubic B-spline basis (splines.py:73-106 recursion, half-open base case):

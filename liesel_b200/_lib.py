@@ -92,6 +92,12 @@ for _sfx in ("f32", "f64"):
     f = getattr(lib, "lslb_mh_step_" + _sfx)
     f.restype = _i
     f.argtypes = [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    f = getattr(lib, "lslb_iwls_group_" + _sfx)
+    f.restype = _i
+    f.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _u32, _vp]
+    f = getattr(lib, "lslb_iwls_propose_diag_" + _sfx)
+    f.restype = _i
+    f.argtypes = [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]
     f = getattr(lib, "lslb_spline_basis_" + _sfx)
     f.restype = _i
     f.argtypes = [_vp, _i64, _vp, _i, _vp, _vp, _vp]
@@ -174,6 +180,7 @@ EXPORTS = [
     "lslb_plan_destroy", "lslb_plan_num_params", "lslb_plan_num_aux", "lslb_plan_dtype", "lslb_plan_block_ncoef", "lslb_plan_variant", "lslb_plan_kernel_name",
     "lslb_workspace_bytes", "lslb_logp_grad_f32", "lslb_logp_grad_f64", "lslb_iwls_f32",
     "lslb_iwls_f64", "lslb_chol_f32", "lslb_chol_f64", "lslb_quadform_f32", "lslb_quadform_f64",
+    "lslb_iwls_group_f32", "lslb_iwls_group_f64", "lslb_iwls_propose_diag_f32", "lslb_iwls_propose_diag_f64",
     "lslb_iwls_propose_f32", "lslb_iwls_propose_f64", "lslb_mh_step_f32", "lslb_mh_step_f64", "lslb_spline_basis_f32",
     "lslb_spline_basis_f64", "lslb_spline_basis_order_f32", "lslb_spline_basis_order_f64",
 ]

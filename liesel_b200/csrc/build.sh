@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
        -I ../../include -Xptxas -v --expt-relaxed-constexpr ${NVCC_EXTRA:-})
-SRCS=(plan.cu tmap.cu tiny.cu logp_grad.cu iwls.cu spline_basis.cu debug.cu banded.cu banded_x2.cu dense_x2.cu banded_iwls_x2.cu dgroup_x2.cu msmooth_x2.cu msort_x2.cu nuts.cu nuts_async.cu dense_tc.cu peer.cu)
+SRCS=(plan.cu tmap.cu tiny.cu logp_grad.cu iwls.cu group_iwls.cu spline_basis.cu debug.cu banded.cu banded_x2.cu dense_x2.cu banded_iwls_x2.cu dgroup_x2.cu msmooth_x2.cu msort_x2.cu nuts.cu nuts_async.cu dense_tc.cu peer.cu)
 # tools library (pipe-peak micro-benchmarks, tcgen05 probe): NOT linked into the product library
 TOOL_SRCS=(microbench.cu tc_probe.cu)
 mkdir -p build

@@ -222,6 +222,7 @@ struct lslb_plan {
   int sm_count;
   int nchunks;
   long long* d_chunk_start;  // device [nchunks+1]
+  int* d_gstart;             // random intercept: device [G + 1], first row of every group (rows sorted by group) or NULL
   double lik_const;
   bool rows_sorted;  // every smooth's knot span changes rarely from row to row
   bool unit_rows;    // every spline row's four weights sum to one (x inside the knot range)

@@ -100,6 +100,17 @@ __global__ void band_diff_kernel(const int* __restrict__ s0, const int* __restri
   if (cnt) atomicAdd(out, cnt);
 }
 
+// gstart[g] = first row whose group index is >= g (rows ascending by group), gstart[G] = n: thread i looks at
+// the boundary between rows i - 1 and i and fills the entries of the groups that start there (a group
+// without rows gets an empty range)
+__global__ void group_starts_kernel(const int* __restrict__ idx, long long n, int G, int* __restrict__ gstart) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const int prev = i == 0 ? -1 : idx[i - 1];
+  const int cur = i == n ? G : idx[i];
+  for (int g = prev + 1; g <= cur; ++g) gstart[g] = (int)i;
+}
+
 // per 128-row tile the sums of the four weight columns of one spline block (one block per tile)
 __global__ void tile_weight_sums_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
   const long long r0 = (long long)blockIdx.x * 128;
@@ -312,6 +323,14 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
     delete p;
     return LSLB_ERR_INVALID;
   }
+  // random intercept: row range of every group, for the diagonal IWLS pass (group_iwls.cu)
+  p->d_gstart = nullptr;
+  if (p->grp >= 0 && e == cudaSuccess && n < 2147483647LL) {
+    const int G = p->blk[p->grp].ncoef;
+    e = cudaMalloc(&p->d_gstart, sizeof(int) * ((size_t)G + 1));
+    if (e == cudaSuccess)
+      group_starts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(p->blk[p->grp].index, n, G, p->d_gstart);
+  }
   // are the rows ordered for long constant-span runs?
   p->rows_sorted = p->ns > 0;
   if (p->ns > 0 && e == cudaSuccess) {
@@ -371,6 +390,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
   if (e != cudaSuccess) {
     set_cuda_error(e, "plan setup kernels");
     cudaFree(p->d_chunk_start);
+    if (p->d_gstart) cudaFree(p->d_gstart);
     delete p;
     return LSLB_ERR_CUDA;
   }
@@ -431,6 +451,7 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
 extern "C" void lslb_plan_destroy(lslb_plan* p) {
   if (!p) return;
   if (p->d_chunk_start) cudaFree(p->d_chunk_start);
+  if (p->d_gstart) cudaFree(p->d_gstart);
   for (int m = 0; m < LSLB_MAX_SPL; ++m)
     if (p->d_tw[m]) cudaFree(p->d_tw[m]);
   for (int m = 0; m < LSLB_MAX_SPL; ++m)

@@ -27,20 +27,31 @@ import math
 
 import torch
 
-from .plan import Plan, chol as chol_info, iwls_propose, mh_step
+from .plan import Plan, chol as chol_info, iwls_propose, iwls_propose_diag, mh_step
 
 
 class IWLSGibbsSampler:
     def __init__(self, plan: Plan, params: torch.Tensor, aux: torch.Tensor | None, seed: int = 0,
                  blocks: list[str] | None = None, initial_step_size: float = 0.01,
                  da_target_accept: float = 0.8, da_gamma: float = 0.05, da_kappa: float = 0.75,
-                 da_t0: int = 10, gibbs: bool = True, constraints: dict | None = None):
+                 da_t0: int = 10, gibbs: bool = True, constraints: dict | None = None,
+                 group_accept: str = "joint"):
         """``constraints``: block name -> ``Z [k, k_r]`` with orthonormal columns (e.g.
         ``reparam.sum_to_zero_basis`` of the basis' column means): the block is sampled in the
         coordinates ``gamma`` of ``beta = Z gamma`` — the constrained design ``B Z`` with penalty
         ``Z' K Z`` that a Liesel user passes to ``add_np_smooth`` for identifiability next to an
         intercept. Score and information transform as ``Z' s`` and ``Z' I Z``; the start values are
-        projected onto the constrained space."""
+        projected onto the constrained space.
+
+        ``group_accept``: how a random-intercept block is accepted. ``"joint"``: one Metropolis-Hastings
+        decision for the whole block, the law of the reference's ``IWLSKernel`` on that block (its acceptance
+        rate, hence the adapted step size, falls with the number of groups). ``"per_group"`` (an extension,
+        not a reference mode): given the other blocks the posterior of b factorises over the groups, so every
+        group is accepted on its own ratio - G independent one-dimensional IWLS kernels in one pass; the step
+        size then does not depend on G."""
+        if group_accept not in ("joint", "per_group"):
+            raise ValueError("group_accept must be 'joint' or 'per_group'")
+        self.group_accept = group_accept
         self.plan, self.spec = plan, plan.spec
         self.params = params.clone().contiguous()
         self.Z = {k: torch.as_tensor(v, dtype=params.dtype, device=params.device).contiguous()
@@ -52,7 +63,9 @@ class IWLSGibbsSampler:
         self.aux = None if aux is None else aux.clone().contiguous()
         self.C = params.shape[0]
         self.dev, self.dt = params.device, params.dtype
-        self.blocks = [b for b in self.spec.blocks if b.kind != 2 and (blocks is None or b.name in blocks)]
+        # a random-intercept block (kind 2) is sampled with the same transition on its DIAGONAL information
+        # (``group_transition``); by default it is part of the sweep like every other coefficient block
+        self.blocks = [b for b in self.spec.blocks if blocks is None or b.name in blocks]
         self.gibbs_blocks = [b for b in self.spec.blocks if gibbs and b.tau2_slot >= 0 and b.prior.ig_a is not None]
         self.gen = torch.Generator(device=self.dev)
         self.gen.manual_seed(seed)
@@ -128,6 +141,65 @@ class IWLSGibbsSampler:
             self._da_step(blk.name, acc, adapt_t)
         return {"error_code": code, "acceptance_prob": acc, "position_moved": accept}
 
+    def group_transition(self, blk, adapt_t: int | None = None):
+        """The IWLS transition for the random-intercept block: score and the diagonal of the information from
+        ``Plan.iwls_group`` (one pass over the rows), ridge / factor / mean / draw / log-density elementwise
+        (``lslb_iwls_propose_diag``). Same law as ``IWLSKernel._standard_transition`` on that block, whose
+        information matrix the reference would form as a dense G x G Hessian."""
+        if self.group_accept == "per_group":
+            return self._group_transition_per_group(blk, adapt_t)
+        sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
+        step = self.step[blk.name]
+        pos = self.params[:, sl].contiguous()
+        score, info = self.plan.iwls_group(self.params, self.aux)
+        z = torch.randn(pos.shape, generator=self.gen, device=self.dev, dtype=self.dt)
+        prop, fwd, code = iwls_propose_diag(pos, score, info, step, z=z)
+        params_prop = self.params.clone()
+        params_prop[:, sl] = prop
+        score_p, info_p = self.plan.iwls_group(params_prop, self.aux)
+        _, bwd, _ = iwls_propose_diag(prop, score_p, info_p, step, x_eval=pos)
+        lp_prop, _ = self.plan.logp_grad(params_prop, self.aux, want_grad=False)
+        self.evals["iwls"] += 2
+        self.evals["logp"] += 1
+        u = torch.rand(self.C, generator=self.gen, device=self.dev, dtype=self.dt)
+        mh_code, acc, accept = mh_step(u, self.logp, lp_prop.contiguous(), (bwd - fwd).contiguous(),
+                                       self.params, params_prop)
+        if adapt_t is not None:
+            self._da_step(blk.name, acc, adapt_t)
+        return {"error_code": code + mh_code, "acceptance_prob": acc, "position_moved": accept}
+
+    def _group_transition_per_group(self, blk, adapt_t):
+        """Every group on its own Metropolis-Hastings ratio: log-posterior share of the group (its rows'
+        log-likelihood + its prior term, ``lslb_iwls_group``'s third output) and the univariate proposal
+        densities (``lslb_iwls_propose_diag`` with the entry-local ridge). The step size stays one number per
+        chain, adapted on the mean acceptance probability over the groups."""
+        sl = slice(blk.param_offset, blk.param_offset + blk.ncoef)
+        step = self.step[blk.name]
+        pos = self.params[:, sl].contiguous()
+        score, info, ll = self.plan.iwls_group(self.params, self.aux, want_loglik=True)
+        z = torch.randn(pos.shape, generator=self.gen, device=self.dev, dtype=self.dt)
+        prop, _, code, fwd = iwls_propose_diag(pos, score, info, step, z=z, elementwise=True)
+        params_prop = self.params.clone()
+        params_prop[:, sl] = prop
+        score_p, info_p, ll_p = self.plan.iwls_group(params_prop, self.aux, want_loglik=True)
+        _, _, _, bwd = iwls_propose_diag(prop, score_p, info_p, step, x_eval=pos, elementwise=True)
+        log_acc = ll_p - ll + bwd - fwd
+        nan = torch.isnan(log_acc)
+        log_acc = torch.where(nan, torch.full_like(log_acc, -float("inf")), log_acc)  # mh.py:53-57, per group
+        acc = torch.exp(torch.clamp(log_acc, max=0.0))
+        u = torch.rand(pos.shape, generator=self.gen, device=self.dev, dtype=self.dt)
+        accept = u <= acc
+        self.params[:, sl] = torch.where(accept, prop, pos)
+        self.logp, _ = self.plan.logp_grad(self.params, self.aux, want_grad=False)
+        self.logp = self.logp.clone()
+        self.evals["iwls"] += 2
+        self.evals["logp"] += 1
+        acc_chain = acc.mean(dim=1)
+        if adapt_t is not None:
+            self._da_step(blk.name, acc_chain, adapt_t)
+        return {"error_code": code + 90 * nan.any(dim=1).to(torch.int32), "acceptance_prob": acc_chain,
+                "position_moved": accept.any(dim=1)}
+
     def gibbs_transition(self, blk):
         """tau2 | beta ~ InverseGamma(a + rank/2, b + beta'K beta/2) (distreg.py:277-297)."""
         pr = blk.prior
@@ -140,7 +212,7 @@ class IWLSGibbsSampler:
     def sweep(self, adapt_t: int | None = None):
         infos = {}
         for blk in self.blocks:
-            infos[blk.name] = self.iwls_transition(blk, adapt_t)
+            infos[blk.name] = (self.group_transition if blk.kind == 2 else self.iwls_transition)(blk, adapt_t)
         if self.gibbs_blocks:
             for blk in self.gibbs_blocks:
                 self.gibbs_transition(blk)

@@ -235,6 +235,25 @@ class Plan:
                               shard.handle, _lib.stream_ptr()), "lslb_iwls_" + shard.transport)
         return score, info, chol
 
+    def iwls_group(self, params, aux=None, flags: int = 0, want_loglik: bool = False):
+        """(score [C,G], info_diag [C,G]) of the random-intercept block: the block's information matrix is
+        diagonal (reference: ``-jacfwd(grad(log_prob))``, ``goose/iwls.py:218-243``, a dense G x G matrix).
+        ``want_loglik``: also each group's share of the log-posterior as a function of its own effect
+        ([C,G]: its rows' log-likelihood + its prior term; the posterior of b factorises over groups)."""
+        Cn = self._check_inputs(params, aux)
+        grp = [b for b in self.spec.blocks if b.kind == 2]
+        if not grp:
+            raise ValueError("the model has no random-intercept block")
+        G = grp[0].ncoef
+        score = torch.empty((Cn, G), dtype=self.dtype, device=self.device)
+        info = torch.empty((Cn, G), dtype=self.dtype, device=self.device)
+        ll = torch.empty((Cn, G), dtype=self.dtype, device=self.device) if want_loglik else None
+        with torch.cuda.device(self.device):
+            fn = getattr(_lib.lib, "lslb_iwls_group_" + _lib.sfx(self.dtype))
+            _lib.check(fn(self._handle, Cn, _lib.ptr(params), _lib.ptr(aux), _lib.ptr(score), _lib.ptr(info),
+                          _lib.ptr(ll), flags, _lib.stream_ptr()), "lslb_iwls_group")
+        return (score, info, ll) if want_loglik else (score, info)
+
     def quadform(self, block: int | str, params):
         """beta^T K beta per chain (``tau2_gibbs_kernel``, reference ``distreg.py:291``)."""
         _lib.require_cuda(params)
@@ -274,6 +293,28 @@ def iwls_propose(beta, score, chol_, step, z=None, x_eval=None):
                       _lib.ptr(z), _lib.ptr(x_eval), _lib.ptr(prop), _lib.ptr(logq),
                       _lib.stream_ptr()), "lslb_iwls_propose")
     return prop, logq
+
+
+def iwls_propose_diag(beta, score, info_diag, step, z=None, x_eval=None, elementwise: bool = False):
+    """
+    :func:`iwls_propose` for a diagonal information matrix (random-intercept block, ``Plan.iwls_group``):
+    returns (prop or None, logq, error_code int32 [C]); code 2 = the ridged diagonal was not positive, identity
+    fallback as ``IWLSKernel._safe_chol`` (``goose/iwls.py:245-290``). ``elementwise``: ridge every entry by
+    1e-6 of itself (its proposal then depends on that entry alone) and return the per-entry log-densities
+    [C, p] as a fourth value.
+    """
+    _lib.require_cuda(beta, score, info_diag, step, z, x_eval)
+    Cn, p = beta.shape
+    prop = torch.empty_like(beta) if z is not None else None
+    logq = torch.empty(Cn, dtype=beta.dtype, device=beta.device)
+    code = torch.empty(Cn, dtype=torch.int32, device=beta.device)
+    el = torch.empty_like(beta) if elementwise else None
+    with torch.cuda.device(beta.device):
+        fn = getattr(_lib.lib, "lslb_iwls_propose_diag_" + _lib.sfx(beta.dtype))
+        _lib.check(fn(Cn, p, _lib.ptr(beta), _lib.ptr(score), _lib.ptr(info_diag), _lib.ptr(step),
+                      _lib.ptr(z), _lib.ptr(x_eval), _lib.ptr(prop), _lib.ptr(logq), _lib.ptr(code),
+                      _lib.ptr(el), 1 if elementwise else 0, _lib.stream_ptr()), "lslb_iwls_propose_diag")
+    return (prop, logq, code, el) if elementwise else (prop, logq, code)
 
 
 def mh_step(u, cur_lp, prop_lp, log_corr=None, params=None, params_prop=None):

@@ -1,9 +1,11 @@
-"""The SAMPLING workloads of BASELINE.json's configs 1-3 on one GPU (the per-call times of the same
+"""The SAMPLING workloads of BASELINE.json's configs 1-3 and 5 on one GPU (the per-call times of the same
 configs are tools/bench_configs.py's): S1 4-chain NUTS on the Bayesian linear regression, S2 NUTS +
 Gibbs tau2 on the 5-smooth P-spline GAM with 64 chains, S3 IWLS blocks + Gibbs tau2 with 256 chains.
+S5 (--configs s5): IWLS blocks for the fixed effects (dense 8 x 8 information) and the random intercept
+(G = 1e5, diagonal information: lslb_iwls_group) of the Poisson model, n = 5e6.
 Asynchronous NUTS driver (liesel_b200/nuts_async.py), reference kernel defaults. One JSON line each.
 
-  python tools/config_samplers.py [--configs s1,s2,s3]
+  python tools/config_samplers.py [--configs s1,s2,s3,s5] [--s5-chains 256]
 """
 import argparse
 import json
@@ -21,6 +23,9 @@ from liesel_b200.plan import Plan  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--configs", default="s1,s2,s3")
+ap.add_argument("--s5-chains", type=int, default=256)
+ap.add_argument("--s5-scale", type=float, default=1.0, help="scales n and G of S5")
+ap.add_argument("--s5-group-accept", default="per_group", choices=["joint", "per_group"])
 args = ap.parse_args()
 want = args.configs.split(",")
 
@@ -76,3 +81,41 @@ if "s3" in want:
                       "ess_bulk_min": float(ess.min()), "ess_bulk_median": float(np.median(ess)),
                       "split_rhat_max": float(np.max(diagnostics.split_rhat_device(draws))),
                       "ess_per_sec_posterior": float(ess.min() / (t2 - t1)), "mean_accept": acc}), flush=True)
+
+if "s5" in want:
+    from liesel_b200.iwls_sampler import IWLSGibbsSampler
+
+    spec, centre = synth.s5_poisson_ri(n=int(5_000_000 * args.s5_scale), G=int(100_000 * args.s5_scale))
+    plan = Plan(spec)
+    C = args.s5_chains
+    th, _ = synth.evaluation_points(spec, centre, C, seed=1)
+    smp = IWLSGibbsSampler(plan, torch.as_tensor(th, device=plan.device), None, seed=1, initial_step_size=0.1,
+                           group_accept=args.s5_group_accept)
+    W, S = 100, 150
+    # P = 100 008 coordinates per chain: keep the fixed effects and 64 evenly spaced random intercepts
+    G = spec.blocks[-1].ncoef
+    keep = torch.as_tensor(np.concatenate([np.arange(8), 8 + np.linspace(0, G - 1, 64).astype(np.int64)]), device=plan.device)
+    t0 = time.perf_counter()
+    smp.warmup(W)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    kept = torch.empty((S, C, keep.numel()), dtype=smp.params.dtype, device=plan.device)
+    accs = {b.name: [] for b in smp.blocks}
+    for t in range(S):
+        infos = smp.sweep()
+        kept[t] = smp.params[:, keep]
+        for k, v in infos.items():
+            accs[k].append(float(v["acceptance_prob"].mean()))
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    ess = diagnostics.ess_bulk_device(kept)
+    print(json.dumps({"config": f"s5: Poisson random intercept n={spec.n} G={G}, IWLS blocks (dense fixed effects + diagonal random intercept), {C} chains",
+                      "chains": C, "warmup": W, "samples": S, "iterations_per_sec": S / (t2 - t1),
+                      "posterior_seconds": t2 - t1, "warmup_seconds": t1 - t0,
+                      "coordinates_summarised": int(keep.numel()), "group_accept": args.s5_group_accept,
+                      "ess_bulk_min": float(ess.min()), "ess_bulk_median": float(np.median(ess)),
+                      "ess_bulk_min_fixed_effects": float(ess[:8].min()), "ess_bulk_min_random_intercepts": float(ess[8:].min()),
+                      "split_rhat_max": float(np.max(diagnostics.split_rhat_device(kept))),
+                      "ess_per_sec_posterior": float(ess.min() / (t2 - t1)),
+                      "step_size_median": {k: float(v.median()) for k, v in smp.step.items()},
+                      "mean_accept": {k: float(np.mean(v)) for k, v in accs.items()}}), flush=True)
