@@ -26,6 +26,8 @@ ap.add_argument("--configs", default="s1,s2,s3")
 ap.add_argument("--s5-chains", type=int, default=256)
 ap.add_argument("--s5-scale", type=float, default=1.0, help="scales n and G of S5")
 ap.add_argument("--s5-group-accept", default="per_group", choices=["joint", "per_group"])
+ap.add_argument("--s5-warmup", type=int, default=100)
+ap.add_argument("--s5-samples", type=int, default=150)
 args = ap.parse_args()
 want = args.configs.split(",")
 
@@ -91,7 +93,7 @@ if "s5" in want:
     th, _ = synth.evaluation_points(spec, centre, C, seed=1)
     smp = IWLSGibbsSampler(plan, torch.as_tensor(th, device=plan.device), None, seed=1, initial_step_size=0.1,
                            group_accept=args.s5_group_accept)
-    W, S = 100, 150
+    W, S = args.s5_warmup, args.s5_samples
     # P = 100 008 coordinates per chain: keep the fixed effects and 64 evenly spaced random intercepts
     G = spec.blocks[-1].ncoef
     keep = torch.as_tensor(np.concatenate([np.arange(8), 8 + np.linspace(0, G - 1, 64).astype(np.int64)]), device=plan.device)

@@ -17,3 +17,6 @@ tail -1 gpurun_out/rec_ref.err
 cat gpurun_out/rec_cfg.jsonl
 (timeout 300 python tools/ess_bench.py --sampler iwls --chains 256 --warmup 100 --samples 100 > gpurun_out/rec_iwls_sampler.json 2> gpurun_out/rec_iwls_sampler.err)
 cat gpurun_out/rec_iwls_sampler.json; tail -2 gpurun_out/rec_iwls_sampler.err
+(timeout 600 python tools/config_samplers.py --configs s1,s2,s3 > gpurun_out/rec_cfg_samplers.jsonl 2> gpurun_out/rec_cfg_samplers.err)
+(timeout 400 python tools/config_samplers.py --configs s5 --s5-chains 256 --s5-warmup 300 --s5-samples 300 >> gpurun_out/rec_cfg_samplers.jsonl 2>> gpurun_out/rec_cfg_samplers.err)
+cat gpurun_out/rec_cfg_samplers.jsonl; tail -2 gpurun_out/rec_cfg_samplers.err
