@@ -276,7 +276,7 @@ def timed_calls(torch, dist, fn, reps, flush, world, dev, warm=3):
 
 # algorithmic flops per batched call (C evaluations) of the secondary configs
 def _flops(name, n, C, p=0):
-    per_row = {"S2": 16 * 5 + 12, "S3": 16 * 2 + 14, "S3_iwls": 8 + 8 + 20 + 8 + 14,
+    per_row = {"S1": 4 * 10 + 14, "S2": 16 * 5 + 12, "S3": 16 * 2 + 14, "S3_iwls": 8 + 8 + 20 + 8 + 14,
                "S4": 4 * p + 12, "S5": 4 * 8 + 10}[name]
     return float(n) * C * per_row
 
@@ -308,17 +308,18 @@ def s3_iwls_sampler(torch, spec, plan, params, aux, warmup=200, samples=300):
 
 
 def secondary_single_gpu(torch, dist, dev, flush, fp32_peak, tf32x3_note, reps=10):
-    """S2, S3 (+ one IWLS pass), one S4 shard and S5 at BASELINE.json's sizes on one GPU."""
+    """S1, S2, S3 (+ one IWLS pass), one S4 shard and S5 (+ IWLS passes of both blocks) at BASELINE.json's sizes on one GPU."""
     from liesel_b200 import synth
     from liesel_b200.plan import Plan
 
     out = []
     cfgs = [
+        ("S1", lambda: synth.s1_blr(n=1000), 4, None, "Bayesian linear regression, n=1000, p=10, 4 chains (launch-latency bound: one launch per call)"),
         ("S2", lambda: synth.s2_pspline_gam(n=100_000), 64, "loc_np0", "P-spline GAM, 5 cubic smooths x 20, n=1e5, 64 chains"),
         ("S3", lambda: synth.s3_gamlss(n=1_000_000), 256, "loc_np0", "Gaussian location-scale GAMLSS, n=1e6, 256 chains"),
         ("S4", lambda: synth.s4_logistic(n=10_000_000, world_size=8), 1024, None,
          "logistic regression p=256: ONE rank's shard of n=1e7 (1.25e6 rows), 1024 chains, no collective at N=1"),
-        ("S5", lambda: synth.s5_poisson_ri(n=5_000_000, G=100_000), 1024, None,
+        ("S5", lambda: synth.s5_poisson_ri(n=5_000_000, G=100_000), 1024, "log_rate_p0",
          "Poisson random intercept, G=1e5, n=5e6, 1024 chains"),
     ]
     for name, make, C, iwls_block, what in cfgs:
@@ -347,6 +348,10 @@ def secondary_single_gpu(torch, dist, dev, flush, fp32_peak, tf32x3_note, reps=1
                 fi = _flops("S3_iwls", spec.n, C)
                 ent["iwls"]["frac_of_fp32_peak"] = fi / (ms_i * 1e-3) / 1e12 / fp32_peak
                 ent["iwls_sampler"] = s3_iwls_sampler(torch, spec, plan, t, a)
+            if name == "S5":  # the random-intercept block: diagonal information (lslb_iwls_group)
+                ms_g = timed_calls(torch, dist, lambda: plan.iwls_group(t, a), reps, flush, 1, dev)
+                ent["iwls_group"] = {"block": "log_rate_ri0", "ms_per_pass": ms_g, "passes_per_s": C / (ms_g * 1e-3),
+                                     "what": "score + diagonal of the observed information of the random-intercept block (G = 1e5)"}
         out.append(ent)
         del plan, t, a
         torch.cuda.empty_cache()

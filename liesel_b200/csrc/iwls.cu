@@ -178,6 +178,94 @@ iwls_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ Iwl
   for (int j = 0; j < q.nq; ++j) out[(size_t)j * p.Cpad] = as[j * TC + tid];
 }
 
+// Dense target with p <= PD <= 8 columns in a "dense block in registers" plan (one dense block, intercepts,
+// optional random intercept: S1 / S5): score [p] and the packed upper triangle [p (p + 1) / 2] of
+// X^T W X accumulate in REGISTERS (44 per chain at p = 8), thread = chain, all lanes read the same row
+// (broadcast loads). iwls_kernel keeps those accumulators in shared memory and pays ~150 shared-memory
+// read-modify-writes per row and chain: 55 ms per pass at S5 with 256 chains (n = 5e6), where the IWLS sweep of
+// that model spends its time. Same partial layout, so reduce / finalize / Cholesky are shared.
+template <typename T, int FAM, int PD, bool GROUP>
+__global__ void __launch_bounds__(128)
+iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ IwlsParams q, int fstride) {
+  const int TC = blockDim.x, tid = threadIdx.x;
+  const int c = blockIdx.y * TC + tid;
+  const DnsP<T>& D = p.dn[0];
+  const size_t ldc = (size_t)p.Cpad;
+  T beta[PD], sc[PD], tri[PD * (PD + 1) / 2];
+#pragma unroll
+  for (int j = 0; j < PD; ++j) {
+    beta[j] = j < D.p ? p.pT[(size_t)(D.soff + j) * ldc + c] : T(0);
+    sc[j] = T(0);
+  }
+#pragma unroll
+  for (int j = 0; j < PD * (PD + 1) / 2; ++j) tri[j] = T(0);
+  T o0 = T(0), o1 = T(0);
+  for (int k = 0; k < p.ni; ++k) {
+    const T v = p.pT[(size_t)p.ic[k].soff * ldc + c];
+    if (p.ic[k].pred) o1 += v; else o0 += v;
+  }
+  const int f0 = blockIdx.x * fstride, f1 = min(f0 + fstride, p.nchunks);
+  const long long r0 = p.chunk_start[f0], r1 = p.chunk_start[f1];
+  int curg = -1;
+  T bg = T(0);
+  for (long long i = r0; i < r1; ++i) {
+    const T* xrow = D.X + i * D.ld;
+    T x[PD];
+    T dot = T(0);
+#pragma unroll
+    for (int j = 0; j < PD; ++j) {
+      x[j] = j < D.p ? __ldg(xrow + j) : T(0);
+      dot = fma(x[j], beta[j], dot);
+    }
+    T eta0 = o0, eta1 = o1;
+    if (D.pred) eta1 += dot; else eta0 += dot;
+    if constexpr (GROUP) {
+      const int g = __ldg(p.gidx + i);
+      if (g != curg) {  // warp-uniform
+        curg = g;
+        bg = p.bT[(size_t)g * ldc + c];
+        if (g + 1 < p.G) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bT + (size_t)(g + 1) * ldc + c));
+      }
+      if (p.gpred) eta1 += bg; else eta0 += bg;
+    }
+    T ll, d0, d1, u0, u1;
+    lik_row<T, FAM, true>(__ldg(p.y + i), eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+    const T r = q.tpred ? d1 : d0;
+    const T W = q.tpred ? u1 : u0;
+    int u = 0;
+#pragma unroll
+    for (int a = 0; a < PD; ++a) {
+      sc[a] = fma(x[a], r, sc[a]);
+      const T xw = x[a] * W;
+#pragma unroll
+      for (int b = a; b < PD; ++b) {
+        tri[u] = fma(xw, x[b], tri[u]);
+        ++u;
+      }
+    }
+  }
+  // accumulator rows as iwls_nq / iwls_kernel lay them out for p = q.p <= PD: score [p], then the packed
+  // upper triangle row by row (the registers hold the PD-wide triangle; entries with b >= p are zero)
+  T* out = reinterpret_cast<T*>(q.partial) + (size_t)blockIdx.x * q.nq * ldc + c;
+#pragma unroll
+  for (int a = 0; a < PD; ++a)
+    if (a < q.p) out[(size_t)a * ldc] = sc[a];
+  {
+    int u = 0, row = q.p;
+#pragma unroll
+    for (int a = 0; a < PD; ++a) {
+#pragma unroll
+      for (int b = a; b < PD; ++b) {
+        if (a < q.p && b < q.p) {
+          out[(size_t)row * ldc] = tri[u];
+          ++row;
+        }
+        ++u;
+      }
+    }
+  }
+}
+
 // sum over the chunk partials of one (row, chain) entry in double, chunk order; eight loads in flight
 // (the plain loop is a chain of nchunks dependent L2 round trips: 592 at the S3 size)
 template <typename T>
@@ -595,10 +683,30 @@ size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
   return best;
 }
 
+// dense target of a "dense block in registers" plan with p <= 8: accumulators in registers
+static bool iwls_dense_reg(const lslb_plan* plan, int tkind, int p) {
+  static const bool off = [] {  // LSLB_NO_IWLS_DENSE_REG=1: the generic kernel (A/B runs)
+    const char* e = getenv("LSLB_NO_IWLS_DENSE_REG");
+    return e && atoi(e) != 0;
+  }();
+  return !off && tkind == TK_DENSE && plan->variant == VAR_DENSE_REG && plan->ns == 0 && plan->nd == 1 && p <= 8;
+}
+
 template <typename T, int FAM>
 static int iwls_dispatch(const lslb_plan* plan, const EvalParams<T>& ep, const IwlsParams& q,
                          const LaunchCfg& k, size_t smem, cudaStream_t st) {
   dim3 grid(k.nchunks, k.ntiles), block(k.TC);
+  if (iwls_dense_reg(plan, q.tkind, q.p)) {
+    if (plan->grp >= 0) {
+      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, true><<<grid, block, 0, st>>>(ep, q, k.fstride);
+      else iwls_dense_reg_kernel<T, FAM, 8, true><<<grid, block, 0, st>>>(ep, q, k.fstride);
+    } else {
+      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, false><<<grid, block, 0, st>>>(ep, q, k.fstride);
+      else iwls_dense_reg_kernel<T, FAM, 8, false><<<grid, block, 0, st>>>(ep, q, k.fstride);
+    }
+    LSLB_LAUNCH_CHECK();
+    return LSLB_OK;
+  }
 #define LSLB_IWLS_LAUNCH(NS, GRP)                                                              \
   do {                                                                                         \
     auto kern = iwls_kernel<T, FAM, NS, GRP>;                                                  \

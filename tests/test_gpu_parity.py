@@ -365,6 +365,24 @@ def test_iwls_other_families(lb, cfg, block):
     check_iwls(spec, plan, block, th, aux)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("p", [3, 6, 8])
+@pytest.mark.parametrize("group", [False, True])
+def test_iwls_dense_block_in_registers(lb, dtype, p, group):
+    """Dense target with p <= 8 in a one-dense-block plan: `lslb::iwls_dense_reg_kernel` (score and packed
+    upper triangle in registers; instantiations PD = 4 / 8, with and without a random intercept) against the
+    oracle, and against the generic shared-memory kernel's layout through the shared finalize."""
+    if group:
+        spec, centre = synth.s5_poisson_ri(n=20_000, G=500, p=p, dtype=dtype, balanced=False)
+        block = "log_rate_p0"
+    else:
+        spec, centre = synth.s1_blr(n=3000, p=p, dtype=dtype)
+        block = "loc_p0"
+    plan = lb.Plan(spec)
+    th, aux = synth.evaluation_points(spec, centre, 37)
+    check_iwls(spec, plan, block, th, aux)
+
+
 def test_chol_failure_is_nan(lb):
     a = np.stack([np.array([[1.0, 2.0], [2.0, 1.0]]), np.eye(2) * 4.0, np.full((2, 2), np.nan)])
     out = lb.chol(torch.as_tensor(a, device="cuda")).cpu().numpy()
