@@ -295,13 +295,23 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
     }
 
     // is every smooth's span constant over this tile? (each warp evaluates it redundantly)
+    // full tiles: the plan stored the answer (the tile's span, or -1) with the tile's weight sums
     bool uni = true;
+    int span0[NSL];
+    if (rows == XR) {
 #pragma unroll
-    for (int m = 0; m < NSL; ++m) {
-      const int first = D.start[m][0];
-      bool eq = true;
-      for (int r = (tid & 31); r < rows; r += 32) eq = eq && (D.start[m][r] == first);
-      uni = uni && __all_sync(0xffffffffu, eq);
+      for (int m = 0; m < NSL; ++m) {
+        span0[m] = __float_as_int(tws[s][m][1]);
+        uni = uni && span0[m] >= 0;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NSL; ++m) {
+        span0[m] = D.start[m][0];
+        bool eq = true;
+        for (int r = (tid & 31); r < rows; r += 32) eq = eq && (D.start[m][r] == span0[m]);
+        uni = uni && __all_sync(0xffffffffu, eq);
+      }
     }
 
     u64 sz2 = pk(0.f, 0.f), se1 = pk(0.f, 0.f);  // per-tile sums: z^2 and eta1 (Normal); see the other families
@@ -441,7 +451,7 @@ banded_x2_kernel(const __grid_constant__ EvalParams<float> p, int tiles_per_cta,
       bool reloaded = false;
 #pragma unroll
       for (int m = 0; m < NS; ++m) {
-        const int first = D.start[(SHW ? 0 : m)][0];
+        const int first = span0[(SHW ? 0 : m)];
         if (first != cur[m]) {
           flush(m);
           load(m, first, fastmode);

@@ -111,19 +111,30 @@ __global__ void group_starts_kernel(const int* __restrict__ idx, long long n, in
   for (int g = prev + 1; g <= cur; ++g) gstart[g] = (int)i;
 }
 
-// per 128-row tile the sums of the four weight columns of one spline block (one block per tile)
-__global__ void tile_weight_sums_kernel(const float* __restrict__ w, long long n, float* __restrict__ out) {
+// per 128-row tile the sums of the four weight columns of one spline block (one block per tile). Entry 1 is
+// not a sum (the closed form of banded_x2.cu needs columns 0, 2, 3 only): it carries, as an int bit pattern,
+// the tile's knot span when all of its rows share one (and the tile is full), else -1 - the kernel's test
+// "is the span constant over this tile" becomes one shared-memory read instead of a loop over the rows
+__global__ void tile_weight_sums_kernel(const float* __restrict__ w, const int* __restrict__ start, long long n,
+                                        float* __restrict__ out) {
   const long long r0 = (long long)blockIdx.x * 128;
   const int u = threadIdx.x & 3, q = threadIdx.x >> 2;  // 32 row slots x 4 columns
   double acc = 0.0;
-  for (int r = q; r < 128 && r0 + r < n; r += 32) acc += (double)w[4 * (r0 + r) + u];
+  const int first = start[r0];
+  int same = 1;
+  for (int r = q; r < 128 && r0 + r < n; r += 32) {
+    acc += (double)w[4 * (r0 + r) + u];
+    same &= start[r0 + r] == first;
+  }
   __shared__ double sh[128];
   sh[threadIdx.x] = acc;
-  __syncthreads();
+  const int all_same = __syncthreads_and(same);
   if (threadIdx.x < 4) {
     double t = 0.0;
     for (int j = 0; j < 32; ++j) t += sh[4 * j + threadIdx.x];  // fixed order
-    out[4 * (long long)blockIdx.x + threadIdx.x] = (float)t;
+    float v = (float)t;
+    if (threadIdx.x == 1) v = __int_as_float((all_same && r0 + 128 <= n) ? first : -1);
+    out[4 * (long long)blockIdx.x + threadIdx.x] = v;
   }
 }
 
@@ -422,7 +433,8 @@ extern "C" int lslb_plan_create(const lslb_model_desc* desc, lslb_plan** out) {
     for (int m = 0; m < p->ns && e == cudaSuccess; ++m) {
       e = cudaMalloc(&p->d_tw[m], sizeof(float) * 4 * ntiles);
       if (e == cudaSuccess)
-        tile_weight_sums_kernel<<<(unsigned)ntiles, 128>>>((const float*)p->blk[p->sp[m]].data, n, p->d_tw[m]);
+        tile_weight_sums_kernel<<<(unsigned)ntiles, 128>>>((const float*)p->blk[p->sp[m]].data, p->blk[p->sp[m]].index, n,
+                                                           p->d_tw[m]);
     }
     // IWLS of the Normal families runs the packed kernel (banded_iwls_x2.cu): weight products of every
     // smooth, 48 bytes per row (LSLB_NO_IWLS_PAIRS=1 skips them; the kernel then multiplies per chain)
