@@ -27,7 +27,7 @@ template <typename T, int FAM>
 __global__ void __launch_bounds__(256)
 group_iwls_kernel(const __grid_constant__ EvalParams<T> p, const int* __restrict__ gstart, const T* __restrict__ params,
                   int P, int goff, int doff, int ioff0, int ioff1, int ioff2, int ioff3, T gm, T ginv_s2,
-                  T* __restrict__ score, T* __restrict__ info, T* __restrict__ llg) {
+                  T* __restrict__ score, T* __restrict__ info, T* __restrict__ llg, int vec) {
   __shared__ T tb[32][33], ts[32][33], tw[32][33], tl[32][33];
   const int g0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -65,9 +65,22 @@ group_iwls_kernel(const __grid_constant__ EvalParams<T> p, const int* __restrict
         T dot = T(0);
         if (p.nd > 0) {
           const T* x = D.X + (size_t)r * D.ld;
+          if (vec) {  // p a multiple of 4, rows 16-byte aligned: one load per four columns
 #pragma unroll
-          for (int j = 0; j < GI_PD; ++j)
-            if (j < D.p) dot = fma(x[j], beta[j], dot);
+            for (int j4 = 0; j4 < GI_PD; j4 += 4) {
+              if (j4 < D.p) {
+                const Vec4<T> v = ld4(x + j4);
+                dot = fma(v.a, beta[j4], dot);
+                dot = fma(v.b, beta[j4 + 1], dot);
+                dot = fma(v.c, beta[j4 + 2], dot);
+                dot = fma(v.d, beta[j4 + 3], dot);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < GI_PD; ++j)
+              if (j < D.p) dot = fma(x[j], beta[j], dot);
+          }
         }
         T e0 = o0, e1 = o1;
         if (p.nd > 0) { if (D.pred) e1 += dot; else e0 += dot; }
@@ -114,10 +127,15 @@ int launch_iwls_group(const lslb_plan* plan, int C, const T* params, const T* au
   for (int q = 0; q < plan->ni; ++q) io[q] = plan->off[plan->ic[q]];
   const int doff = plan->nd ? plan->off[plan->dn[0]] : 0;
   const int G = d.ncoef;
+  int vec = 0;
+  if (plan->nd == 1) {
+    const lslb_block_desc& dd = plan->blk[plan->dn[0]];
+    vec = dd.ncoef % 4 == 0 && dd.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(dd.data) & (4 * sizeof(T) - 1)) == 0;
+  }
   dim3 grid((G + 31) / 32, (C + 31) / 32), block(32, 8);
 #define LSLB_GI_GO(F)                                                                                        \
   group_iwls_kernel<T, F><<<grid, block, 0, st>>>(ep, plan->d_gstart, params, plan->P, plan->off[plan->grp], doff, \
-                                                  io[0], io[1], io[2], io[3], (T)d.prior_m, inv_s2, score, info, llg)
+                                                  io[0], io[1], io[2], io[3], (T)d.prior_m, inv_s2, score, info, llg, vec)
   switch (plan->fam) {
     case FAM_NORMAL_LS: LSLB_GI_GO(FAM_NORMAL_LS); break;
     case FAM_NORMAL_FIXED: LSLB_GI_GO(FAM_NORMAL_FIXED); break;

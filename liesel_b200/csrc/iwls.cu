@@ -186,7 +186,8 @@ iwls_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ Iwl
 // that model spends its time. Same partial layout, so reduce / finalize / Cholesky are shared.
 template <typename T, int FAM, int PD, bool GROUP>
 __global__ void __launch_bounds__(128)
-iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ IwlsParams q, int fstride) {
+iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_constant__ IwlsParams q, int fstride,
+                      int vec /* rows are PD wide, 16-byte aligned: vector loads */) {
   const int TC = blockDim.x, tid = threadIdx.x;
   const int c = blockIdx.y * TC + tid;
   const DnsP<T>& D = p.dn[0];
@@ -212,11 +213,18 @@ iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_cons
     const T* xrow = D.X + i * D.ld;
     T x[PD];
     T dot = T(0);
+    if (vec) {  // (ten scalar loads per row and warp made the load unit the bottleneck: 2-3 vector loads)
 #pragma unroll
-    for (int j = 0; j < PD; ++j) {
-      x[j] = j < D.p ? __ldg(xrow + j) : T(0);
-      dot = fma(x[j], beta[j], dot);
+      for (int j4 = 0; j4 < PD; j4 += 4) {
+        const Vec4<T> v = ld4(xrow + j4);
+        x[j4] = v.a; x[j4 + 1] = v.b; x[j4 + 2] = v.c; x[j4 + 3] = v.d;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < PD; ++j) x[j] = j < D.p ? __ldg(xrow + j) : T(0);
     }
+#pragma unroll
+    for (int j = 0; j < PD; ++j) dot = fma(x[j], beta[j], dot);
     T eta0 = o0, eta1 = o1;
     if (D.pred) eta1 += dot; else eta0 += dot;
     if constexpr (GROUP) {
@@ -697,12 +705,15 @@ static int iwls_dispatch(const lslb_plan* plan, const EvalParams<T>& ep, const I
                          const LaunchCfg& k, size_t smem, cudaStream_t st) {
   dim3 grid(k.nchunks, k.ntiles), block(k.TC);
   if (iwls_dense_reg(plan, q.tkind, q.p)) {
+    const lslb_block_desc& d = plan->blk[plan->dn[0]];
+    const int pd = q.p <= 4 ? 4 : 8;
+    const int vec = d.ncoef == pd && d.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.data) & (4 * sizeof(T) - 1)) == 0;
     if (plan->grp >= 0) {
-      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, true><<<grid, block, 0, st>>>(ep, q, k.fstride);
-      else iwls_dense_reg_kernel<T, FAM, 8, true><<<grid, block, 0, st>>>(ep, q, k.fstride);
+      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, true><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
+      else iwls_dense_reg_kernel<T, FAM, 8, true><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
     } else {
-      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, false><<<grid, block, 0, st>>>(ep, q, k.fstride);
-      else iwls_dense_reg_kernel<T, FAM, 8, false><<<grid, block, 0, st>>>(ep, q, k.fstride);
+      if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, false><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
+      else iwls_dense_reg_kernel<T, FAM, 8, false><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
     }
     LSLB_LAUNCH_CHECK();
     return LSLB_OK;
