@@ -29,7 +29,10 @@ group_iwls_kernel(const __grid_constant__ EvalParams<T> p, const int* __restrict
                   int P, int goff, int doff, int ioff0, int ioff1, int ioff2, int ioff3, T gm, T ginv_s2,
                   T* __restrict__ score, T* __restrict__ info, T* __restrict__ llg, int vec) {
   __shared__ T tb[32][33], ts[32][33], tw[32][33], tl[32][33];
-  const int g0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  // chain tiles vary fastest in the grid: the CTAs that walk the same groups' rows run together and share
+  // them through L2 (with the group tile fastest every chain tile re-read all rows from DRAM: 6.2 GB per pass
+  // at S5 with 1024 chains against 0.2 GB of rows, ncu profiles/r02_s5_iwls_kernels_full.md)
+  const int g0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int G = p.G, C = p.C;
   // b tile: params[c0 + cl][goff + g0 + tx] -> tb[cl][tx]
@@ -132,7 +135,8 @@ int launch_iwls_group(const lslb_plan* plan, int C, const T* params, const T* au
     const lslb_block_desc& dd = plan->blk[plan->dn[0]];
     vec = dd.ncoef % 4 == 0 && dd.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(dd.data) & (4 * sizeof(T) - 1)) == 0;
   }
-  dim3 grid((G + 31) / 32, (C + 31) / 32), block(32, 8);
+  if ((G + 31) / 32 > 65535) return LSLB_ERR_UNSUPPORTED;  // grid.y
+  dim3 grid((C + 31) / 32, (G + 31) / 32), block(32, 8);
 #define LSLB_GI_GO(F)                                                                                        \
   group_iwls_kernel<T, F><<<grid, block, 0, st>>>(ep, plan->d_gstart, params, plan->P, plan->off[plan->grp], doff, \
                                                   io[0], io[1], io[2], io[3], (T)d.prior_m, inv_s2, score, info, llg, vec)

@@ -209,26 +209,39 @@ iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_cons
   const long long r0 = p.chunk_start[f0], r1 = p.chunk_start[f1];
   int curg = -1;
   T bg = T(0);
-  for (long long i = r0; i < r1; ++i) {
+  // one row of look-ahead in registers: the loads of row i + 1 are in flight while row i computes (without it
+  // the warp waited out an L1/L2 round trip per row: long-scoreboard 3.2 stall cycles per issued instruction)
+  auto load_row = [&](long long i, T (&xr)[PD], T& yr, int& gr) {
     const T* xrow = D.X + i * D.ld;
-    T x[PD];
-    T dot = T(0);
     if (vec) {  // (ten scalar loads per row and warp made the load unit the bottleneck: 2-3 vector loads)
 #pragma unroll
       for (int j4 = 0; j4 < PD; j4 += 4) {
         const Vec4<T> v = ld4(xrow + j4);
-        x[j4] = v.a; x[j4 + 1] = v.b; x[j4 + 2] = v.c; x[j4 + 3] = v.d;
+        xr[j4] = v.a; xr[j4 + 1] = v.b; xr[j4 + 2] = v.c; xr[j4 + 3] = v.d;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < PD; ++j) x[j] = j < D.p ? __ldg(xrow + j) : T(0);
+      for (int j = 0; j < PD; ++j) xr[j] = j < D.p ? __ldg(xrow + j) : T(0);
     }
+    yr = __ldg(p.y + i);
+    gr = GROUP ? __ldg(p.gidx + i) : 0;
+  };
+  T xn[PD], yn = T(0);
+  int gn = 0;
+  if (r0 < r1) load_row(r0, xn, yn, gn);
+  for (long long i = r0; i < r1; ++i) {
+    T x[PD];
+#pragma unroll
+    for (int j = 0; j < PD; ++j) x[j] = xn[j];
+    const T yv = yn;
+    const int g = gn;
+    if (i + 1 < r1) load_row(i + 1, xn, yn, gn);
+    T dot = T(0);
 #pragma unroll
     for (int j = 0; j < PD; ++j) dot = fma(x[j], beta[j], dot);
     T eta0 = o0, eta1 = o1;
     if (D.pred) eta1 += dot; else eta0 += dot;
     if constexpr (GROUP) {
-      const int g = __ldg(p.gidx + i);
       if (g != curg) {  // warp-uniform
         curg = g;
         bg = p.bT[(size_t)g * ldc + c];
@@ -236,8 +249,9 @@ iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_cons
       }
       if (p.gpred) eta1 += bg; else eta0 += bg;
     }
+    (void)g;
     T ll, d0, d1, u0, u1;
-    lik_row<T, FAM, true>(__ldg(p.y + i), eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+    lik_row<T, FAM, true>(yv, eta0, eta1, p.fixed_inv_scale, ll, d0, d1, u0, u1);
     const T r = q.tpred ? d1 : d0;
     const T W = q.tpred ? u1 : u0;
     int u = 0;

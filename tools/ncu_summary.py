@@ -2,6 +2,7 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/r01_launches.md
   python tools/ncu_summary.py full gpurun_out/prof.ncu-rep profiles/r01_banded_x2_full.md [traffic.json key]
+  python tools/ncu_summary.py full gpurun_out/prof.raw.csv profiles/...md      (raw page exported on the box)
 """
 import collections
 import csv
@@ -72,7 +73,12 @@ def launches(src, dst):
 
 
 def full(src, dst, traffic_key=None):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: an .ncu-rep, or the CSV of its raw page already exported on the GPU box
+    # (`ncu -i x.ncu-rep --page raw --csv > x.raw.csv`: reports with source can exceed what gpurun brings back)
+    if src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     H, U = rows[0], rows[1]
     out = []
