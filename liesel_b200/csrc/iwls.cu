@@ -675,6 +675,15 @@ static bool iwls_fast(const lslb_plan* plan, int tkind) {
          (tkind == TK_SPLINE || tkind == TK_INTERCEPT);
 }
 
+// dense target of a "dense block in registers" plan with p <= 8: accumulators in registers
+static bool iwls_dense_reg(const lslb_plan* plan, int tkind, int p) {
+  static const bool off = [] {  // LSLB_NO_IWLS_DENSE_REG=1: the generic kernel (A/B runs)
+    const char* e = getenv("LSLB_NO_IWLS_DENSE_REG");
+    return e && atoi(e) != 0;
+  }();
+  return !off && tkind == TK_DENSE && plan->variant == VAR_DENSE_REG && plan->ns == 0 && plan->nd == 1 && p <= 8;
+}
+
 static LaunchCfg iwls_cfg(const lslb_plan* plan, int C, int tkind, int nq) {
   if (iwls_fast(plan, tkind)) {
     BandedCfg b = banded_iwls_cfg(plan, C);
@@ -686,7 +695,15 @@ static LaunchCfg iwls_cfg(const lslb_plan* plan, int C, int tkind, int nq) {
     k.nchunks = b.nchunks;
     return k;
   }
-  return choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+  LaunchCfg k = choose_cfg(plan, C, iwls_smem_per_chain(plan, nq));
+  if (tkind == TK_DENSE && plan->nd == 1 && iwls_dense_reg(plan, tkind, plan->blk[plan->dn[0]].ncoef) && k.fstride > 8) {
+    // iwls_dense_reg_kernel sums a whole row chunk in fp32 registers: at most 8 fine chunks (n / (16 SMs'
+    // worth) rows each: 17k rows at S5) per accumulator, whatever the chain count - the regime the full-size
+    // parity test covers (test_full_size_s5_iwls_both_blocks); the chunk partials are summed in double
+    k.fstride = 8;
+    k.nchunks = (plan->nchunks + k.fstride - 1) / k.fstride;
+  }
+  return k;
 }
 
 size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
@@ -703,15 +720,6 @@ size_t iwls_workspace_bytes(const lslb_plan* plan, int C) {
     if (bytes > best) best = bytes;
   }
   return best;
-}
-
-// dense target of a "dense block in registers" plan with p <= 8: accumulators in registers
-static bool iwls_dense_reg(const lslb_plan* plan, int tkind, int p) {
-  static const bool off = [] {  // LSLB_NO_IWLS_DENSE_REG=1: the generic kernel (A/B runs)
-    const char* e = getenv("LSLB_NO_IWLS_DENSE_REG");
-    return e && atoi(e) != 0;
-  }();
-  return !off && tkind == TK_DENSE && plan->variant == VAR_DENSE_REG && plan->ns == 0 && plan->nd == 1 && p <= 8;
 }
 
 template <typename T, int FAM>

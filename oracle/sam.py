@@ -288,6 +288,41 @@ def iwls(spec, block_name, params, aux=None, work_dtype=np.float64, prep=None):
     return score, info
 
 
+def iwls_group_diag(spec, block_name, params, aux=None, work_dtype=np.float64, prep=None):
+    """
+    ``iwls`` for a random-intercept block with the information returned as its DIAGONAL [C, G] (the dense
+    matrix ``iwls`` builds for the same block is diagonal; at G = 1e5 it cannot be formed). Also returns each
+    group's share of the log-posterior [C, G]: its rows' log-likelihood terms (without the row constants)
+    minus (b_g - m)^2 / (2 s^2).
+    """
+    prep = prep or Prepared(spec, work_dtype)
+    dt = prep.dt
+    params = np.atleast_2d(np.asarray(params, dtype=dt))
+    C = params.shape[0]
+    ent = next(e for e in prep.blocks if e["blk"].name == block_name)
+    blk = ent["blk"]
+    assert blk.kind == KIND_GROUP
+    G = blk.ncoef
+    sl = slice(blk.param_offset, blk.param_offset + G)
+    score = np.zeros((C, G), dtype=dt)
+    diag = np.zeros((C, G), dtype=dt)
+    share = np.zeros((C, G), dtype=dt)
+    for c in range(C):
+        theta = params[c]
+        eta = prep.predictors(theta)
+        ll, d1, w = prep.lik_terms(eta)
+        score[c] = np.bincount(ent["idx"], weights=d1[blk.predictor], minlength=G)
+        diag[c] = np.bincount(ent["idx"], weights=w[blk.predictor], minlength=G)
+        share[c] = np.bincount(ent["idx"], weights=ll, minlength=G)
+        pr = blk.prior
+        if pr is not None:
+            d = theta[sl] - pr.m
+            score[c] -= d / (pr.s * pr.s)
+            diag[c] += 1.0 / (pr.s * pr.s)
+            share[c] -= 0.5 * d * d / (pr.s * pr.s)
+    return score, diag, share
+
+
 def quadform(spec, block_name, params, work_dtype=np.float64):
     """beta^T K beta per chain: the Gibbs update's ``beta @ K @ beta`` (distreg.py:291)."""
     blk = next(b for b in spec.blocks if b.name == block_name)

@@ -845,6 +845,33 @@ def test_iwls_sampler_with_random_intercept_block(lb, group_accept):
     np.testing.assert_allclose(a.std(axis=(0, 1)), sd, rtol=0.1)
 
 
+def test_full_size_s5_iwls_both_blocks(lb):
+    """BASELINE config 5 at size (n = 5e6, G = 1e5, 256 chains): the IWLS pass of the fixed-effects block
+    (`iwls_dense_reg_kernel`: fp32 register accumulators over n / chunks rows each - the thing small-n parity
+    cannot vouch for) and of the random-intercept block (`group_iwls_kernel`) against the fp64 oracle on three
+    chains. Same tolerance formulas as the small cases."""
+    spec, centre = synth.s5_poisson_ri(n=5_000_000, G=100_000)
+    plan = lb.Plan(spec)
+    C = 256
+    th, aux = synth.evaluation_points(spec, centre, C)
+    sel = [0, 100, C - 1]
+    check_iwls(spec, plan, "log_rate_p0", th, aux, chains=sel)
+    # 1024 chains: four times fewer row chunks would fit the SMs; the launch keeps the rows per accumulator
+    th4 = np.concatenate([th, th, th, th])
+    check_iwls(spec, plan, "log_rate_p0", th4, np.concatenate([aux] * 4), chains=[3, 700, 1023])
+    t = dev(th, plan)
+    score, diag, share = plan.iwls_group(t, want_loglik=True)
+    prep = sam.Prepared(spec)
+    r_score, r_diag, r_share = sam.iwls_group_diag(spec, "log_rate_ri0", th[sel], None, prep=prep)
+    np.testing.assert_allclose(diag.cpu().numpy()[sel], r_diag, rtol=3e-5)
+    np.testing.assert_allclose(score.cpu().numpy()[sel], r_score, rtol=3e-5, atol=3e-5 * np.abs(r_diag).max())
+    # shares: the device leaves the row constants out, so compare differences between chains
+    sh = share.cpu().numpy()[sel].astype(np.float64)
+    d_dev, d_ref = sh[1:] - sh[:1], r_share[1:] - r_share[:1]
+    scale = np.abs(r_share).max()
+    assert np.all(np.abs(d_dev - d_ref) <= 3e-5 * np.abs(d_ref) + 16 * 2.0**-24 * scale)
+
+
 # --- BASELINE.json full sizes: size-independent properties -------------------------------------------
 def test_full_size_h_properties(lb):
     """H (n = 1e6, 1024 chains): the oracle would take minutes, so check properties instead:

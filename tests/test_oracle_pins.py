@@ -420,3 +420,38 @@ def test_tutorial_01b_model_log_prob_pins(golden_dir):
         if "log_prior" in want:
             assert sam.log_prob(spec, th)[0] - parts["response"][0] == pytest.approx(want["log_prior"], rel=3e-7)
             assert parts["response"][0] == pytest.approx(want["log_lik"], rel=3e-7)
+
+
+def test_group_block_information_is_diagonal_and_shares_add_up():
+    """The random-intercept block: the dense information `sam.iwls` forms (what the reference's
+    `-jacfwd(grad(log_prob))` gives, goose/iwls.py:218-243) is diagonal and equals `sam.iwls_group_diag`;
+    the score is the log-posterior's gradient (finite differences); moving ONE group's effect changes the
+    log-posterior by exactly the change of that group's share."""
+    spec, centre = synth.s5_poisson_ri(n=3000, G=40, dtype=np.float64, balanced=False)
+    th, aux = synth.evaluation_points(spec, centre, 2)
+    name = "log_rate_ri0"
+    blk = spec.block(name)
+    s_dense, i_dense = sam.iwls(spec, name, th, aux)
+    s_diag, i_diag, share = sam.iwls_group_diag(spec, name, th, aux)
+    assert np.array_equal(s_dense, s_diag)
+    assert np.array_equal(np.diagonal(i_dense, axis1=1, axis2=2), i_diag)
+    assert np.all(i_dense - i_diag[:, :, None] * np.eye(blk.ncoef) == 0)
+    g = 7
+    h = 1e-5
+    tp, tm = th.copy(), th.copy()
+    tp[:, blk.param_offset + g] += h
+    tm[:, blk.param_offset + g] -= h
+    lp_p, lp_m = sam.log_prob(spec, tp, aux), sam.log_prob(spec, tm, aux)
+    np.testing.assert_allclose((lp_p - lp_m) / (2 * h), s_diag[:, g], rtol=1e-6)
+    lp0 = sam.log_prob(spec, th, aux)
+    h2 = 1e-3  # (a wider step for the second difference: rounding of the log-posterior / h^2)
+    tp2, tm2 = th.copy(), th.copy()
+    tp2[:, blk.param_offset + g] += h2
+    tm2[:, blk.param_offset + g] -= h2
+    second = -(sam.log_prob(spec, tp2, aux) - 2 * lp0 + sam.log_prob(spec, tm2, aux)) / h2**2
+    np.testing.assert_allclose(second, i_diag[:, g], rtol=1e-4)
+    _, _, share_p = sam.iwls_group_diag(spec, name, tp, aux)
+    np.testing.assert_allclose(share_p[:, g] - share[:, g], lp_p - lp0, rtol=1e-8, atol=1e-9)
+    mask = np.ones(blk.ncoef, dtype=bool)
+    mask[g] = False
+    assert np.array_equal(share_p[:, mask], share[:, mask])
