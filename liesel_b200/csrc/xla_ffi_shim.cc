@@ -148,6 +148,31 @@ ffi::Error IwlsImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, int64_t 
   return ffi::Error::Success();
 }
 
+// score + DIAGONAL of the observed information of the random-intercept block (lslb_iwls_group_*): what an
+// IWLSKernel whose position is that block obtains from grad / -jacfwd(grad) (goose/iwls.py:206-243), without
+// the G x G matrix
+template <ffi::DataType DT>
+ffi::Error IwlsGroupImpl(cudaStream_t stream, int64_t plan_handle, ffi::Buffer<DT> params, ffi::Buffer<DT> aux,
+                         ffi::ResultBuffer<DT> score, ffi::ResultBuffer<DT> info_diag) {
+  const lslb_plan* plan = reinterpret_cast<const lslb_plan*>(plan_handle);
+  int C = 0;
+  ffi::Error e = check_common<DT>(plan, params, aux, &C);
+  if (e.failure()) return e;
+  const auto sd = score->dimensions();
+  if (sd.size() != 2 || sd[0] != C || sd[1] < 1) return Invalid("score must be [C, G]");
+  if (!dims_are(info_diag->dimensions(), {sd[0], sd[1]})) return Invalid("info_diag must be [C, G]");
+  const Native<DT>* ax = lslb_plan_num_aux(plan) > 0 ? aux.typed_data() : nullptr;
+  int st;
+  if constexpr (DT == ffi::F32)
+    st = lslb_iwls_group_f32(plan, C, params.typed_data(), ax, score->typed_data(), info_diag->typed_data(), nullptr,
+                             0u, reinterpret_cast<lslb_stream_t>(stream));
+  else
+    st = lslb_iwls_group_f64(plan, C, params.typed_data(), ax, score->typed_data(), info_diag->typed_data(), nullptr,
+                             0u, reinterpret_cast<lslb_stream_t>(stream));
+  if (st != LSLB_OK) return ffi::Error(ffi::ErrorCode::kInternal, lslb_status_string(st));
+  return ffi::Error::Success();
+}
+
 // beta^T K beta of one penalised block (tau2_gibbs_kernel, model/distreg.py:291)
 template <ffi::DataType DT>
 ffi::Error QuadformImpl(cudaStream_t stream, int64_t plan_handle, int64_t block, ffi::Buffer<DT> params,
@@ -199,6 +224,14 @@ ffi::Error QuadformImpl(cudaStream_t stream, int64_t plan_handle, int64_t block,
       .Ret<ffi::Buffer<DT>>()                       \
       .Ret<ffi::Buffer<DT>>()                       \
       .Ret<ffi::Buffer<DT>>()
+#define LSLB_BIND_IWLS_GROUP(DT)                    \
+  ffi::Ffi::Bind()                                  \
+      .Ctx<ffi::PlatformStream<cudaStream_t>>()     \
+      .Attr<int64_t>("plan")                        \
+      .Arg<ffi::Buffer<DT>>()                       \
+      .Arg<ffi::Buffer<DT>>()                       \
+      .Ret<ffi::Buffer<DT>>()                       \
+      .Ret<ffi::Buffer<DT>>()
 #define LSLB_BIND_QUADFORM(DT)                      \
   ffi::Ffi::Bind()                                  \
       .Ctx<ffi::PlatformStream<cudaStream_t>>()     \
@@ -213,6 +246,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbLogp, LogpImpl<ffi::F32>, LSLB_BIND_LOGP(ffi::
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbLogpF64, LogpImpl<ffi::F64>, LSLB_BIND_LOGP(ffi::F64));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbIwls, IwlsImpl<ffi::F32>, LSLB_BIND_IWLS(ffi::F32));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbIwlsF64, IwlsImpl<ffi::F64>, LSLB_BIND_IWLS(ffi::F64));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbIwlsGroup, IwlsGroupImpl<ffi::F32>, LSLB_BIND_IWLS_GROUP(ffi::F32));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbIwlsGroupF64, IwlsGroupImpl<ffi::F64>, LSLB_BIND_IWLS_GROUP(ffi::F64));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbQuadform, QuadformImpl<ffi::F32>, LSLB_BIND_QUADFORM(ffi::F32));
 XLA_FFI_DEFINE_HANDLER_SYMBOL(LslbQuadformF64, QuadformImpl<ffi::F64>, LSLB_BIND_QUADFORM(ffi::F64));
 

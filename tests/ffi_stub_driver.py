@@ -6,7 +6,7 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STUB_SO = os.path.join(ROOT, "liesel_b200", "csrc", "build", "liblslb_xla_ffi_stub.so")
 HANDLERS = ["LslbLogpGrad", "LslbLogpGradF64", "LslbLogp", "LslbLogpF64", "LslbIwls", "LslbIwlsF64",
-            "LslbQuadform", "LslbQuadformF64"]
+            "LslbQuadform", "LslbQuadformF64", "LslbIwlsGroup", "LslbIwlsGroupF64"]
 F32, F64 = 11, 12
 OK, INVALID_ARGUMENT, INTERNAL = 0, 3, 13
 

@@ -101,3 +101,32 @@ def test_shim_model_without_aux():
                          [drv.tensor_buf(lp), drv.tensor_buf(g)])
     assert code == drv.OK, msg
     assert torch.equal(lp, lp0) and torch.equal(g, g0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_shim_group_iwls_handler_equals_the_c_abi(dtype):
+    """`LslbIwlsGroup`: score and diagonal information of the random-intercept block through the stub call
+    frame, bit for bit what `Plan.iwls_group` (ctypes) returns; shape checks without touching the GPU."""
+    from liesel_b200.plan import Plan
+
+    lib = drv.load()
+    sfx = "" if dtype == np.float32 else "F64"
+    spec, centre = synth.s5_poisson_ri(n=20_000, G=300, dtype=dtype, balanced=False)
+    plan = Plan(spec)
+    C_ = 21
+    th, _ = synth.evaluation_points(spec, centre, C_)
+    t = torch.as_tensor(th, device=plan.device)
+    a = torch.empty((C_, 0), dtype=t.dtype, device=plan.device)
+    s0, i0 = plan.iwls_group(t)
+    torch.cuda.synchronize()
+    h = plan._handle.value
+    s1, i1 = torch.empty_like(s0), torch.empty_like(i0)
+    code, msg = drv.call(lib, "LslbIwlsGroup" + sfx, h, [drv.tensor_buf(t), drv.tensor_buf(a)],
+                         [drv.tensor_buf(s1), drv.tensor_buf(i1)])
+    assert code == drv.OK, msg
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s0) and torch.equal(i1, i0)
+    code, msg = drv.call(lib, "LslbIwlsGroup" + sfx, h, [drv.tensor_buf(t), drv.tensor_buf(a)],
+                         [drv.tensor_buf(s1), drv.tensor_buf(i1, shape=(C_, 299))])
+    assert code == drv.INVALID_ARGUMENT and "info_diag" in msg
