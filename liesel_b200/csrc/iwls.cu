@@ -7,6 +7,7 @@
 // (src/liesel/model/distreg.py:291).
 #include "common.cuh"
 #include "prologue.cuh"
+#include "x2_common.cuh"
 
 namespace lslb {
 
@@ -286,6 +287,97 @@ iwls_dense_reg_kernel(const __grid_constant__ EvalParams<T> p, const __grid_cons
       }
     }
   }
+}
+
+// The same with TWO chains per thread and packed FP32 math (float32 plans whose rows are PD wide and 16-byte
+// aligned): the row's values are scalars shared by both chains (broadcast operands of the packed FMAs), so a
+// row costs ~75 instructions per chain PAIR instead of ~100 per chain (the scalar kernel is issue-bound).
+// 64 threads = 128 chains per CTA, the scalar launch geometry otherwise; same partial layout.
+template <int FAM, int PD, bool GROUP>
+__global__ void __launch_bounds__(64)
+iwls_dense_reg_x2_kernel(const __grid_constant__ EvalParams<float> p, const __grid_constant__ IwlsParams q, int fstride) {
+  const int tid = threadIdx.x;
+  const int c = 2 * (blockIdx.y * blockDim.x + tid);  // first of this thread's two chains (< Cpad, even)
+  const DnsP<float>& D = p.dn[0];
+  const size_t ldc = (size_t)p.Cpad;
+  auto ld2 = [&](const float* base, size_t row) -> u64 { return *reinterpret_cast<const u64*>(base + row * ldc + c); };
+  const u64 ZERO = pk(0.f, 0.f);
+  u64 beta[PD], sc[PD], tri[PD * (PD + 1) / 2];
+#pragma unroll
+  for (int j = 0; j < PD; ++j) {
+    beta[j] = ld2(p.pT, (size_t)(D.soff + j));
+    sc[j] = ZERO;
+  }
+#pragma unroll
+  for (int j = 0; j < PD * (PD + 1) / 2; ++j) tri[j] = ZERO;
+  u64 o0 = ZERO, o1 = ZERO;
+  for (int k = 0; k < p.ni; ++k) {
+    const u64 v = ld2(p.pT, (size_t)p.ic[k].soff);
+    if (p.ic[k].pred) o1 = add2(o1, v); else o0 = add2(o0, v);
+  }
+  const int f0 = blockIdx.x * fstride, f1 = min(f0 + fstride, p.nchunks);
+  const long long r0 = p.chunk_start[f0], r1 = p.chunk_start[f1];
+  int curg = -1;
+  u64 bg = ZERO;
+  auto load_row = [&](long long i, float (&xr)[PD], float& yr, int& gr) {
+    const float* xrow = D.X + i * D.ld;
+#pragma unroll
+    for (int j4 = 0; j4 < PD; j4 += 4) {
+      const Vec4<float> v = ld4(xrow + j4);
+      xr[j4] = v.a; xr[j4 + 1] = v.b; xr[j4 + 2] = v.c; xr[j4 + 3] = v.d;
+    }
+    yr = __ldg(p.y + i);
+    gr = GROUP ? __ldg(p.gidx + i) : 0;
+  };
+  float xn[PD], yn = 0.f;
+  int gn = 0;
+  if (r0 < r1) load_row(r0, xn, yn, gn);
+  for (long long i = r0; i < r1; ++i) {
+    float x[PD];
+#pragma unroll
+    for (int j = 0; j < PD; ++j) x[j] = xn[j];
+    const float yv = yn;
+    const int g = gn;
+    if (i + 1 < r1) load_row(i + 1, xn, yn, gn);
+    u64 dot = ZERO;
+#pragma unroll
+    for (int j = 0; j < PD; ++j) dot = fma2(bc(x[j]), beta[j], dot);
+    u64 eta0 = o0, eta1 = o1;
+    if (D.pred) eta1 = add2(eta1, dot); else eta0 = add2(eta0, dot);
+    if constexpr (GROUP) {
+      if (g != curg) {  // warp-uniform
+        curg = g;
+        bg = ld2(p.bT, (size_t)g);
+        if (g + 1 < p.G) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bT + (size_t)(g + 1) * ldc + c));
+      }
+      if (p.gpred) eta1 = add2(eta1, bg); else eta0 = add2(eta0, bg);
+    }
+    (void)g;
+    float e0a, e0b, e1a, e1b, ll, d0, d1, u0, u1;
+    upk(eta0, e0a, e0b);
+    upk(eta1, e1a, e1b);
+    lik_row<float, FAM, true>(yv, e0a, e1a, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+    const float ra = q.tpred ? d1 : d0, Wa = q.tpred ? u1 : u0;
+    lik_row<float, FAM, true>(yv, e0b, e1b, p.fixed_inv_scale, ll, d0, d1, u0, u1);
+    const u64 r = pk(ra, q.tpred ? d1 : d0), W = pk(Wa, q.tpred ? u1 : u0);
+    int u = 0;
+#pragma unroll
+    for (int a = 0; a < PD; ++a) {
+      const u64 xa = bc(x[a]);
+      sc[a] = fma2(xa, r, sc[a]);
+      const u64 xw = mul2(xa, W);
+#pragma unroll
+      for (int b = a; b < PD; ++b) {
+        tri[u] = fma2(bc(x[b]), xw, tri[u]);
+        ++u;
+      }
+    }
+  }
+  float* out = reinterpret_cast<float*>(q.partial) + (size_t)blockIdx.x * q.nq * ldc + c;
+#pragma unroll
+  for (int a = 0; a < PD; ++a) *reinterpret_cast<u64*>(out + (size_t)a * ldc) = sc[a];
+#pragma unroll
+  for (int j = 0; j < PD * (PD + 1) / 2; ++j) *reinterpret_cast<u64*>(out + (size_t)(PD + j) * ldc) = tri[j];
 }
 
 // sum over the chunk partials of one (row, chain) entry in double, chunk order; eight loads in flight
@@ -730,6 +822,26 @@ static int iwls_dispatch(const lslb_plan* plan, const EvalParams<T>& ep, const I
     const lslb_block_desc& d = plan->blk[plan->dn[0]];
     const int pd = q.p <= 4 ? 4 : 8;
     const int vec = d.ncoef == pd && d.ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.data) & (4 * sizeof(T) - 1)) == 0;
+    static const bool no_x2 = [] {  // LSLB_NO_IWLS_DENSE_X2=1: the scalar kernel (A/B runs)
+      const char* e = getenv("LSLB_NO_IWLS_DENSE_X2");
+      return e && atoi(e) != 0;
+    }();
+    if constexpr (sizeof(T) == 4) {
+      // rows exactly PD wide (q.p == PD): the register triangle IS the layout. From 512 chains: A/B at S5 on one
+      // box, ms per pass: 1024 chains 24.8 -> 21.3, 256 chains 6.68 -> 6.81 (no gain: not issue-bound there)
+      if (vec && !no_x2 && k.TC % 64 == 0 && k.Cpad >= 512) {
+        dim3 block2(k.TC / 2);
+        if (plan->grp >= 0) {
+          if (pd == 4) iwls_dense_reg_x2_kernel<FAM, 4, true><<<grid, block2, 0, st>>>(ep, q, k.fstride);
+          else iwls_dense_reg_x2_kernel<FAM, 8, true><<<grid, block2, 0, st>>>(ep, q, k.fstride);
+        } else {
+          if (pd == 4) iwls_dense_reg_x2_kernel<FAM, 4, false><<<grid, block2, 0, st>>>(ep, q, k.fstride);
+          else iwls_dense_reg_x2_kernel<FAM, 8, false><<<grid, block2, 0, st>>>(ep, q, k.fstride);
+        }
+        LSLB_LAUNCH_CHECK();
+        return LSLB_OK;
+      }
+    }
     if (plan->grp >= 0) {
       if (q.p <= 4) iwls_dense_reg_kernel<T, FAM, 4, true><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
       else iwls_dense_reg_kernel<T, FAM, 8, true><<<grid, block, 0, st>>>(ep, q, k.fstride, vec);
