@@ -381,6 +381,9 @@ def test_iwls_dense_block_in_registers(lb, dtype, p, group):
     plan = lb.Plan(spec)
     th, aux = synth.evaluation_points(spec, centre, 37)
     check_iwls(spec, plan, block, th, aux)
+    if p == 8 and dtype == np.float32:  # from 512 chains: the packed twin `iwls_dense_reg_x2_kernel`
+        th, aux = synth.evaluation_points(spec, centre, 512)
+        check_iwls(spec, plan, block, th, aux, chains=[0, 1, 300, 511])
 
 
 def test_chol_failure_is_nan(lb):
