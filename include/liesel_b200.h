@@ -185,7 +185,9 @@ int lslb_iwls_f64(const lslb_plan* plan, int C, int block, const double* params,
  *                       rows' log-likelihood terms (without the row constants) - (b_g - m)^2 / (2 s^2).
  *                       Given the other blocks the posterior of b factorises over the groups, so these
  *                       are what a group-by-group Metropolis-Hastings step needs (iwls_sampler.py).
- * No workspace. LSLB_SKIP_PRIOR leaves the prior terms out (row-sharded ranks > 0).
+ * No workspace. LSLB_SKIP_PRIOR leaves the prior terms out (row-sharded ranks > 0): all three outputs are
+ * sums over rows, so under row sharding the caller adds them over the ranks (there is no _peer / _nccl
+ * variant of this entry point; sharding BY GROUP needs no sum at all).
  */
 int lslb_iwls_group_f32(const lslb_plan* plan, int C, const float* params, const float* aux,
                         float* score, float* info_diag, float* loglik_group, uint32_t flags,
