@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):
-    if name in ("Plan", "chol", "iwls_propose"):
+    if name in ("Plan", "chol", "iwls_propose", "iwls_propose_diag", "mh_step"):
         from . import plan as _plan
 
         return getattr(_plan, name)
